@@ -1,0 +1,90 @@
+// K9 + the M_ctx = 1 cross-attention fast path: everything that is loop-invariant, run ONCE per sample() call
+// (SURVEY.md 0.3, 0.4, D.3).  All fp32, tiny; one warp per output feature.
+//   fourier_embed : sigma -> [sigma, sin(2 pi sigma w), cos(2 pi sigma w)]       (TimeConditioningPlugin, a3)
+//   linear_act    : out[r, j] = act_out(dot(act_in(in[r, :]), W[j, :]) + bias[j])  (time MLP, Modulation / SkipModulate
+//                   Linear(SiLU(features)) tables, cross-attention V and out projections)
+//   ln_rows       : affine LayerNorm of the embedding rows (Attention.norm_context, a10)
+#pragma once
+#include "ptx.cuh"
+
+namespace sfb {
+
+__global__ void fourier_embed_kernel(const float* __restrict__ sigma, const float* __restrict__ w, float* __restrict__ out,
+                                     int rows, int half) {
+  const int r = blockIdx.x;
+  const int i = threadIdx.x;
+  if (r >= rows) return;
+  const float t = sigma[r];
+  float* o = out + (size_t)r * (2 * half + 1);
+  if (i == 0) o[0] = t;
+  if (i < half) {
+    const float f = t * w[i] * 6.283185307179586f;
+    o[1 + i] = sinf(f);
+    o[1 + half + i] = cosf(f);
+  }
+}
+
+// LinearSchedule: torch.linspace(1, 0, steps) in fp32 (ATen's two-sided formula)
+__global__ void sigma_linspace_kernel(float* __restrict__ out, int steps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= steps) return;
+  const float start = 1.f, end = 0.f;
+  const float step = (end - start) / (float)(steps - 1);
+  out[i] = i < steps / 2 ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+}
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.7071067811865476f));
+  if (act == ACT_SILU) return v / (1.f + expf(-v));
+  return v;
+}
+
+// in [rows, K], W [J, K] (row pitch ldw), out [rows, ldo] at column offset; one warp per output feature j.
+__global__ void __launch_bounds__(256) linear_act_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int rows,
+                                                         int K, int J, int ldw, int ldo, int act_in, int act_out) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= J) return;
+  const float* wr = W + (size_t)j * ldw;
+  const float bj = bias ? bias[j] : 0.f;
+  for (int r = 0; r < rows; ++r) {
+    const float* ir = in + (size_t)r * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc += act_apply(ir[k], act_in) * wr[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(size_t)r * ldo + j] = act_apply(acc + bj, act_out);
+  }
+}
+
+// in [rows, C] -> out [rows, C] = LN(in) * gamma + beta ; one warp per row
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float* __restrict__ out, int rows, int C,
+                                                      float eps) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* ir = in + (size_t)r * C;
+  float s = 0.f;
+  for (int k = lane; k < C; k += 32) s += ir[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int k = lane; k < C; k += 32) { const float d = ir[k] - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  for (int k = lane; k < C; k += 32) out[(size_t)r * C + k] = (ir[k] - mean) * rstd * gamma[k] + beta[k];
+}
+
+// Build the effective embedding rows for the CFG-doubled batch: rows [0, B) = embedding, rows [B, 2B) = fixed row.
+__global__ void build_emb_rows_kernel(const float* __restrict__ emb, const float* __restrict__ fixed, float* __restrict__ out,
+                                      int B, int Beff, int F) {
+  const int r = blockIdx.x;
+  for (int k = threadIdx.x; k < F; k += blockDim.x) out[(size_t)r * F + k] = (r < B) ? emb[(size_t)r * F + k] : fixed[k];
+}
+
+}  // namespace sfb

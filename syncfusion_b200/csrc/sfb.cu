@@ -1,0 +1,1107 @@
+// libsyncfusion_b200.so - C ABI (include/syncfusion_b200.h), weight re-packing, execution plan and launch logic
+// for the SyncFusion U-Net v-diffusion sampling loop on sm_100a.  See DESIGN.md for the data layout and the plan.
+//
+// Reference path being replaced (all in /root/reference): main/generation.py:77-83 and
+// main/module_diffusion.py:200-206 call DiffusionModel.sample(); the architecture is exp/model/diffusion.yaml:11-33;
+// the arithmetic (audio_diffusion_pytorch / a_unet) is restated in oracle/ (SURVEY.md Appendix A).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/syncfusion_b200.h"
+#include "attn_tc.cuh"
+#include "d0.cuh"
+#include "elementwise.cuh"
+#include "gemm_tc.cuh"
+#include "prepare.cuh"
+
+using namespace sfb;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ utilities
+struct HostTensor {
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <typename T> CUtensorMapDataType tmap_dtype();
+template <> CUtensorMapDataType tmap_dtype<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
+template <> CUtensorMapDataType tmap_dtype<float>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
+
+// rank-3 map over a contiguous [d2][d1][d0] tensor (d0 innermost), 128B swizzle, zero OOB fill.
+template <typename T>
+bool make_tmap3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * sizeof(T), d0 * d1 * sizeof(T)};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return fn(m, tmap_dtype<T>(), 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <typename T>
+bool make_tmap2(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {d0 * sizeof(T)};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t es[2] = {1, 1};
+  return fn(m, tmap_dtype<T>(), 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T> T host_cvt(float v);
+template <> float host_cvt<float>(float v) { return v; }
+template <> __nv_bfloat16 host_cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct GemmW {           // re-packed weights of one contraction
+  void* w = nullptr;     // [taps * N][Kw] operand precision
+  float* bias = nullptr; // [bias_mod] or null
+  int N = 0, K1 = 0, K2 = 0, taps = 1, bias_mod = 0;
+};
+
+struct ItemW {
+  float *gn1_g = nullptr, *gn1_b = nullptr, *gn2_g = nullptr, *gn2_b = nullptr;
+  GemmW conv1, conv2, inject, qkv, out;
+  float *c8_w1 = nullptr, *c8_b1 = nullptr, *c8_w2 = nullptr, *c8_b2 = nullptr, *c8_wi = nullptr, *c8_bi = nullptr;
+  bool has_attn = false, has_xattn = false, has_inject = false;
+  float *x_ng = nullptr, *x_nb = nullptr, *x_wv = nullptr, *x_wo = nullptr;
+  int mod_off = 0, xb_off = 0;
+};
+struct DepthW {
+  GemmW down, up;
+  float *c8_dw = nullptr, *c8_db = nullptr, *c8_uw = nullptr;
+  float c8_ub = 0.f;
+  int up_taps = 1;
+  std::vector<ItemW> items[2];
+  int skip_off = 0;
+};
+
+enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN };
+const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn"};
+
+struct EngineBase {
+  sfb_unet_config cfg;
+  int device = 0;
+  std::string err;
+  std::map<std::string, HostTensor> params;
+  bool finalized = false;
+  int op_limit = -1;
+  int64_t launches = 0;
+  virtual ~EngineBase() {}
+  virtual int finalize() = 0;
+  virtual int workspace_bytes(int64_t B, int64_t L, int cfg_on, int64_t rows, size_t* out) = 0;
+  virtual int unet_forward(const float* x, const float* sigma, const float* const* channels, int n_channels,
+                           const float* embedding, int64_t M, float scale, float* v_out, int64_t B, int64_t L, void* ws,
+                           size_t ws_bytes, cudaStream_t st) = 0;
+  virtual int sample(const float* x_noisy, int num_steps, const float* const* channels, int n_channels,
+                     const float* embedding, int64_t M, float scale, float* x_out, float* traj_x, float* traj_v,
+                     const float* teacher_x, int64_t B, int64_t L, void* ws, size_t ws_bytes, cudaStream_t st) = 0;
+  virtual int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes) = 0;
+  virtual int op_info(int i, char* buf, int len) = 0;
+  int fail(int code, const char* fmt, ...) {
+    char b[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(b, sizeof b, fmt, ap);
+    va_end(ap);
+    err = b;
+    return code;
+  }
+};
+
+#define SFB_CUDA(call)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(SFB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+template <typename T, int BN>
+void launch_gemm_bn(const GemmParams<T>& p, int B, cudaStream_t st) {
+  dim3 grid(B * p.tiles_per_clip, p.N / BN);
+  gemm_tc_kernel<T, BN><<<grid, kGemmThreads, gemm_smem_bytes<T, BN>(), st>>>(p);
+}
+template <typename T>
+void launch_gemm(const GemmParams<T>& p, int BN, int B, cudaStream_t st) {
+  switch (BN) {
+    case 32: launch_gemm_bn<T, 32>(p, B, st); break;
+    case 64: launch_gemm_bn<T, 64>(p, B, st); break;
+    case 128: launch_gemm_bn<T, 128>(p, B, st); break;
+    default: launch_gemm_bn<T, 256>(p, B, st); break;
+  }
+}
+template <typename T>
+cudaError_t set_kernel_attrs() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<T, 32>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<T, 64>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<T, 128>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<T, 256>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attn_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<T>());
+  return e;
+}
+int pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  if (N == 64) return 64;
+  if (N == 32) return 32;
+  return 0;
+}
+
+template <typename T>
+bool fill_gemm_maps(GemmParams<T>& p, const void* a1, int K1, int L, int B, const void* a2, int K2, int B2, const void* w,
+                    int N, int taps, int BN) {
+  constexpr int BK = ElemTraits<T>::kAtomElems;
+  if (!make_tmap3<T>(&p.tmA1, a1, K1, L, B, BK, kGemmBM)) return false;
+  if (K2 > 0) {
+    if (!make_tmap3<T>(&p.tmA2, a2, K2, L, B2, BK, kGemmBM)) return false;
+  } else {
+    p.tmA2 = p.tmA1;
+  }
+  if (!make_tmap2<T>(&p.tmW, w, (uint64_t)(K1 + K2), (uint64_t)taps * N, BK, BN)) return false;
+  p.rows_per_clip = L;
+  p.tiles_per_clip = (L + kGemmBM - 1) / kGemmBM;
+  p.N = N;
+  p.taps = taps;
+  p.k1_chunks = (K1 + BK - 1) / BK;
+  p.k2_chunks = K2 > 0 ? (K2 + BK - 1) / BK : 0;
+  p.K1 = K1;
+  p.a2_bmod = B2 > 0 ? B2 : 1;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+template <typename T>
+struct Engine : EngineBase {
+  std::vector<void*> owned;
+  std::vector<DepthW> dw;
+  // conditioning weights (fp32)
+  float *t_w = nullptr, *t_lw = nullptr, *t_lb = nullptr, *t_mw = nullptr, *t_mb = nullptr, *fixed_emb = nullptr;
+  float *ft_w = nullptr, *ft_b = nullptr;   // concatenated Linear(SiLU(features)) weights [F_total][MF]
+  int F_total = 0, XB_total = 0, n_gn = 0;
+
+  struct Op {
+    int kind = 0, depth = 0, stack = 0, item = 0;
+    const void* in = nullptr;
+    const void* in2 = nullptr;
+    void* out_t = nullptr;
+    float* out_r = nullptr;
+    const float* resid = nullptr;
+    double* stats_in = nullptr;
+    double* stats_out = nullptr;
+    const float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
+    float fscalar = 0.f;
+    int L = 0, C = 0, gs = 0, B = 0, taps = 1, in_is_f32 = 0, ctx = 0;
+    int ft_off = -1;      // feature-table column offset (Modulation scale | SkipModulate scale), -1: none
+    GemmParams<T> gp;
+    AttnParams<T> ap;
+    int BN = 0;
+    size_t dbg_off = 0, dbg_bytes = 0;
+    int dbg_rows = 0, dbg_cols = 0, dbg_dtype = 0;
+  };
+  struct WsLayout {
+    size_t sigma, embrows, tmp1, tmp2, fourier, h1, h2, feat, ftable, xbias, stats, stats_bytes, veff, xstate, total;
+    size_t ctx[SFB_MAX_DEPTH], bufA[SFB_MAX_DEPTH], T1[SFB_MAX_DEPTH], T2[SFB_MAX_DEPTH], qkv[SFB_MAX_DEPTH], o[SFB_MAX_DEPTH];
+  };
+  struct Plan {
+    int64_t B = 0, L = 0;
+    int cfg_on = 0;
+    void* ws = nullptr;
+    WsLayout lay;
+    std::vector<Op> ops;
+  };
+  Plan plan;
+
+  ~Engine() override {
+    for (void* p : owned) cudaFree(p);
+  }
+
+  // ---------------------------------------------------------------- parameter access
+  const HostTensor* get(const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = params.find(name);
+    if (it == params.end()) {
+      fail(SFB_ERR_MISSING, "missing parameter '%s'", name.c_str());
+      return nullptr;
+    }
+    std::vector<int64_t> s(shape);
+    if (it->second.shape != s) {
+      std::string got;
+      for (auto d : it->second.shape) got += std::to_string(d) + ",";
+      std::string want;
+      for (auto d : s) want += std::to_string(d) + ",";
+      fail(SFB_ERR_INVALID, "parameter '%s' has shape [%s], expected [%s]", name.c_str(), got.c_str(), want.c_str());
+      return nullptr;
+    }
+    return &it->second;
+  }
+  template <typename U>
+  U* upload(const std::vector<U>& h) {
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(h.size() * sizeof(U), 16)) != cudaSuccess) return nullptr;
+    owned.push_back(d);
+    if (cudaMemcpy(d, h.data(), h.size() * sizeof(U), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    return reinterpret_cast<U*>(d);
+  }
+  float* upload_f(const HostTensor* t) { return t ? upload<float>(t->v) : nullptr; }
+  void* upload_T(const std::vector<float>& w) {
+    std::vector<T> h(w.size());
+    for (size_t i = 0; i < w.size(); ++i) h[i] = host_cvt<T>(w[i]);
+    return upload<T>(h);
+  }
+
+  // conv weight [Co][Ci][taps] -> [taps*Co][Ci]
+  bool pack_conv3(const std::string& base, int C, GemmW& g) {
+    const HostTensor* w = get(base + ".weight", {C, C, 3});
+    const HostTensor* b = get(base + ".bias", {C});
+    if (!w || !b) return false;
+    std::vector<float> r((size_t)3 * C * C);
+    for (int co = 0; co < C; ++co)
+      for (int ci = 0; ci < C; ++ci)
+        for (int t = 0; t < 3; ++t) r[((size_t)t * C + co) * C + ci] = w->v[((size_t)co * C + ci) * 3 + t];
+    g.w = upload_T(r);
+    g.bias = upload_f(b);
+    g.N = C; g.K1 = C; g.K2 = 0; g.taps = 3; g.bias_mod = C;
+    return g.w && g.bias;
+  }
+
+  int finalize() override {
+    const sfb_unet_config& c = cfg;
+    const int D = c.depth, MF = c.modulation_features, EF = c.embedding_features;
+    const int mid = c.attention_heads * c.attention_features;
+    if (c.in_channels != 1) return fail(SFB_ERR_UNSUPPORTED, "in_channels must be 1");
+    if (c.channels[0] != 8) return fail(SFB_ERR_UNSUPPORTED, "channels[0] must be 8 (depth-0 streaming kernels)");
+    if (c.factors[0] != 1) return fail(SFB_ERR_UNSUPPORTED, "factors[0] must be 1");
+    if (c.attention_heads != 8 || c.attention_features != 64)
+      return fail(SFB_ERR_UNSUPPORTED, "attention must be 8 heads x 64");
+    if (c.resnet_groups != 8) return fail(SFB_ERR_UNSUPPORTED, "resnet_groups must be 8");
+    if (c.context_channels[0] != 2) return fail(SFB_ERR_UNSUPPORTED, "context_channels[0] must be 2");
+    for (int d = 1; d < D; ++d) {
+      if (!pick_bn(c.channels[d])) return fail(SFB_ERR_UNSUPPORTED, "channels[%d]=%d must be 32, 64 or a multiple of 128", d, c.channels[d]);
+      if (c.context_channels[d] <= 0 || c.context_channels[d] % 8) return fail(SFB_ERR_UNSUPPORTED, "context_channels[%d] must be a positive multiple of 8", d);
+      if (!pick_bn(c.factors[d] * c.channels[d - 1])) return fail(SFB_ERR_UNSUPPORTED, "factors[%d]*channels[%d] must be 32, 64 or a multiple of 128", d, d - 1);
+    }
+    if (c.attentions[0]) return fail(SFB_ERR_UNSUPPORTED, "self-attention at depth 0 unsupported");
+    if (set_kernel_attrs<T>() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+
+    // time conditioning (A.3)
+    t_w = upload_f(get("time.weights", {128}));
+    t_lw = upload_f(get("time.linear.weight", {MF, 257}));
+    t_lb = upload_f(get("time.linear.bias", {MF}));
+    t_mw = upload_f(get("time.mlp.weight", {MF, MF}));
+    t_mb = upload_f(get("time.mlp.bias", {MF}));
+    fixed_emb = upload_f(get("fixed_embedding.weight", {c.embedding_max_length, EF}));
+    if (!t_w || !t_lw || !t_lb || !t_mw || !t_mb || !fixed_emb) return err.empty() ? fail(SFB_ERR_CUDA, "upload failed") : SFB_ERR_MISSING;
+
+    std::vector<float> ftw, ftb;   // concatenated feature linears
+    dw.assign(D, DepthW());
+    F_total = 0; XB_total = 0;
+    for (int d = 0; d < D; ++d) {
+      const int C = c.channels[d], Cin = d == 0 ? c.in_channels : c.channels[d - 1], f = c.factors[d], ctx = c.context_channels[d];
+      DepthW& W = dw[d];
+      char pre[64];
+      snprintf(pre, sizeof pre, "d%d.", d);
+      const std::string P(pre);
+      // ---- Down (A.6)
+      {
+        const HostTensor* w = get(P + "down.weight", {C, Cin, f});
+        const HostTensor* b = get(P + "down.bias", {C});
+        if (!w || !b) return SFB_ERR_MISSING;
+        if (d == 0) {
+          W.c8_dw = upload_f(w); W.c8_db = upload_f(b);
+        } else {
+          std::vector<float> r((size_t)C * f * Cin);
+          for (int co = 0; co < C; ++co)
+            for (int ci = 0; ci < Cin; ++ci)
+              for (int j = 0; j < f; ++j) r[(size_t)co * f * Cin + j * Cin + ci] = w->v[((size_t)co * Cin + ci) * f + j];
+          W.down.w = upload_T(r); W.down.bias = upload_f(b);
+          W.down.N = C; W.down.K1 = f * Cin; W.down.taps = 1; W.down.bias_mod = C;
+        }
+      }
+      // ---- Up (A.6, both modes)
+      if (c.upsample_mode == SFB_UPSAMPLE_TRANSPOSE) {
+        const HostTensor* w = get(P + "up.weight", {C, Cin, f});
+        const HostTensor* b = get(P + "up.bias", {Cin});
+        if (!w || !b) return SFB_ERR_MISSING;
+        W.up_taps = 1;
+        if (d == 0) {
+          std::vector<float> r(8);
+          for (int ci = 0; ci < 8; ++ci) r[ci] = w->v[ci];
+          W.c8_uw = upload<float>(r); W.c8_ub = b->v[0];
+        } else {
+          std::vector<float> r((size_t)f * Cin * C);
+          for (int ci = 0; ci < C; ++ci)
+            for (int co = 0; co < Cin; ++co)
+              for (int j = 0; j < f; ++j) r[((size_t)j * Cin + co) * C + ci] = w->v[((size_t)ci * Cin + co) * f + j];
+          W.up.w = upload_T(r); W.up.bias = upload_f(b);
+          W.up.N = f * Cin; W.up.K1 = C; W.up.taps = 1; W.up.bias_mod = Cin;
+        }
+      } else {
+        const HostTensor* w = get(P + "up.conv.weight", {Cin, C, 3});
+        const HostTensor* b = get(P + "up.conv.bias", {Cin});
+        if (!w || !b) return SFB_ERR_MISSING;
+        W.up_taps = 3;
+        if (d == 0) {
+          std::vector<float> r(24);
+          for (int t = 0; t < 3; ++t)
+            for (int ci = 0; ci < 8; ++ci) r[t * 8 + ci] = w->v[(size_t)ci * 3 + t];
+          W.c8_uw = upload<float>(r); W.c8_ub = b->v[0];
+        } else {
+          // nearest xf + conv3 at the fine resolution == conv3 at the coarse resolution with N = f*Cin outputs:
+          // fine position l*f + j, tap t reads coarse position l + floor((j + t - 1) / f).
+          const int N = f * Cin;
+          std::vector<float> r((size_t)3 * N * C, 0.f);
+          for (int j = 0; j < f; ++j)
+            for (int t = 0; t < 3; ++t) {
+              const int num = j + t - 1;
+              const int o = num < 0 ? -1 : num / f;    // floor division
+              for (int co = 0; co < Cin; ++co)
+                for (int ci = 0; ci < C; ++ci)
+                  r[((size_t)(o + 1) * N + j * Cin + co) * C + ci] += w->v[((size_t)co * C + ci) * 3 + t];
+            }
+          W.up.w = upload_T(r); W.up.bias = upload_f(b);
+          W.up.N = N; W.up.K1 = C; W.up.taps = 3; W.up.bias_mod = Cin;
+        }
+      }
+      // ---- SkipModulate Linear (A.5)
+      {
+        const HostTensor* w = get(P + "skip.weight", {Cin, MF});
+        const HostTensor* b = get(P + "skip.bias", {Cin});
+        if (!w || !b) return SFB_ERR_MISSING;
+        W.skip_off = F_total;
+        ftw.insert(ftw.end(), w->v.begin(), w->v.end());
+        ftb.insert(ftb.end(), b->v.begin(), b->v.end());
+        F_total += Cin;
+      }
+      // ---- items
+      for (int s = 0; s < 2; ++s) {
+        W.items[s].assign(c.items[d], ItemW());
+        for (int i = 0; i < c.items[d]; ++i) {
+          ItemW& I = W.items[s][i];
+          char ip[96];
+          snprintf(ip, sizeof ip, "d%d.items_%s.%d.", d, s == 0 ? "down" : "up", i);
+          const std::string Q(ip);
+          I.gn1_g = upload_f(get(Q + "resnet.gn1.weight", {C}));
+          I.gn1_b = upload_f(get(Q + "resnet.gn1.bias", {C}));
+          I.gn2_g = upload_f(get(Q + "resnet.gn2.weight", {C}));
+          I.gn2_b = upload_f(get(Q + "resnet.gn2.bias", {C}));
+          if (!I.gn1_g || !I.gn1_b || !I.gn2_g || !I.gn2_b) return SFB_ERR_MISSING;
+          if (d == 0) {
+            for (int k = 0; k < 2; ++k) {
+              const HostTensor* w = get(Q + (k ? "resnet.conv2.weight" : "resnet.conv1.weight"), {8, 8, 3});
+              const HostTensor* b = get(Q + (k ? "resnet.conv2.bias" : "resnet.conv1.bias"), {8});
+              if (!w || !b) return SFB_ERR_MISSING;
+              std::vector<float> r(192);
+              for (int co = 0; co < 8; ++co)
+                for (int ci = 0; ci < 8; ++ci)
+                  for (int t = 0; t < 3; ++t) r[(t * 8 + ci) * 8 + co] = w->v[(co * 8 + ci) * 3 + t];
+              (k ? I.c8_w2 : I.c8_w1) = upload<float>(r);
+              (k ? I.c8_b2 : I.c8_b1) = upload_f(b);
+            }
+          } else {
+            if (!pack_conv3(Q + "resnet.conv1", C, I.conv1) || !pack_conv3(Q + "resnet.conv2", C, I.conv2))
+              return err.empty() ? fail(SFB_ERR_CUDA, "weight upload failed") : SFB_ERR_MISSING;
+          }
+          {  // Modulation Linear(MF -> 2C)
+            const HostTensor* w = get(Q + "mod.linear.weight", {2 * C, MF});
+            const HostTensor* b = get(Q + "mod.linear.bias", {2 * C});
+            if (!w || !b) return SFB_ERR_MISSING;
+            I.mod_off = F_total;
+            ftw.insert(ftw.end(), w->v.begin(), w->v.end());
+            ftb.insert(ftb.end(), b->v.begin(), b->v.end());
+            F_total += 2 * C;
+          }
+          I.has_inject = ctx > 0;
+          if (I.has_inject) {
+            const HostTensor* w = get(Q + "inject.conv.weight", {C, C + ctx, 1});
+            const HostTensor* b = get(Q + "inject.conv.bias", {C});
+            if (!w || !b) return SFB_ERR_MISSING;
+            if (d == 0) {
+              std::vector<float> r((size_t)(8 + ctx) * 8);
+              for (int co = 0; co < 8; ++co)
+                for (int k = 0; k < 8 + ctx; ++k) r[k * 8 + co] = w->v[(size_t)co * (8 + ctx) + k];
+              I.c8_wi = upload<float>(r); I.c8_bi = upload_f(b);
+            } else {
+              I.inject.w = upload_T(w->v); I.inject.bias = upload_f(b);
+              I.inject.N = C; I.inject.K1 = C; I.inject.K2 = ctx; I.inject.taps = 1; I.inject.bias_mod = C;
+            }
+          } else {
+            return fail(SFB_ERR_UNSUPPORTED, "context_channels[%d] == 0 unsupported", d);
+          }
+          I.has_attn = c.attentions[d] != 0;
+          if (I.has_attn) {
+            const HostTensor* g1 = get(Q + "attn.attn.norm.weight", {C});
+            const HostTensor* b1 = get(Q + "attn.attn.norm.bias", {C});
+            const HostTensor* g2 = get(Q + "attn.attn.norm_ctx.weight", {C});
+            const HostTensor* b2 = get(Q + "attn.attn.norm_ctx.bias", {C});
+            const HostTensor* wq = get(Q + "attn.attn.to_q.weight", {mid, C});
+            const HostTensor* wkv = get(Q + "attn.attn.to_kv.weight", {2 * mid, C});
+            const HostTensor* wo = get(Q + "attn.attn.to_out.weight", {C, mid});
+            if (!g1 || !b1 || !g2 || !b2 || !wq || !wkv || !wo) return SFB_ERR_MISSING;
+            // fold the two LayerNorm affines into the fused QKV projection: W' = W diag(g), bias' = W b
+            std::vector<float> r((size_t)3 * mid * C), bb(3 * mid);
+            for (int n = 0; n < 3 * mid; ++n) {
+              const bool isq = n < mid;
+              const float* wr = isq ? &wq->v[(size_t)n * C] : &wkv->v[(size_t)(n - mid) * C];
+              const std::vector<float>& g = isq ? g1->v : g2->v;
+              const std::vector<float>& bt = isq ? b1->v : b2->v;
+              double acc = 0;
+              for (int k = 0; k < C; ++k) {
+                r[(size_t)n * C + k] = wr[k] * g[k];
+                acc += (double)wr[k] * bt[k];
+              }
+              bb[n] = (float)acc;
+            }
+            I.qkv.w = upload_T(r); I.qkv.bias = upload<float>(bb);
+            I.qkv.N = 3 * mid; I.qkv.K1 = C; I.qkv.taps = 1; I.qkv.bias_mod = 3 * mid;
+            I.out.w = upload_T(wo->v); I.out.bias = nullptr;
+            I.out.N = C; I.out.K1 = mid; I.out.taps = 1; I.out.bias_mod = C;
+          }
+          I.has_xattn = c.cross_attentions[d] != 0;
+          if (I.has_xattn) {
+            // M_ctx = 1 fast path: softmax over one key == 1, so the item is x + W_o V(LN_ctx(e)).
+            const HostTensor* g = get(Q + "xattn.attn.norm_ctx.weight", {EF});
+            const HostTensor* b = get(Q + "xattn.attn.norm_ctx.bias", {EF});
+            const HostTensor* wkv = get(Q + "xattn.attn.to_kv.weight", {2 * mid, EF});
+            const HostTensor* wo = get(Q + "xattn.attn.to_out.weight", {C, mid});
+            if (!g || !b || !wkv || !wo) return SFB_ERR_MISSING;
+            // (norm / to_q of the query side provably do not influence the output when M_ctx = 1; they are
+            //  still required to be present so a full state_dict loads without surprises.)
+            if (!get(Q + "xattn.attn.to_q.weight", {mid, C}) || !get(Q + "xattn.attn.norm.weight", {C}) ||
+                !get(Q + "xattn.attn.norm.bias", {C}))
+              return SFB_ERR_MISSING;
+            std::vector<float> wv(wkv->v.begin() + (size_t)mid * EF, wkv->v.end());
+            I.x_ng = upload_f(g); I.x_nb = upload_f(b); I.x_wv = upload<float>(wv); I.x_wo = upload_f(wo);
+            I.xb_off = XB_total;
+            XB_total += C;
+          }
+        }
+      }
+    }
+    ft_w = upload<float>(ftw);
+    ft_b = upload<float>(ftb);
+    if (!ft_w || !ft_b) return fail(SFB_ERR_CUDA, "upload failed");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SFB_ERR_CUDA, "finalize: %s", cudaGetErrorString(e));
+    finalized = true;
+    params.clear();
+    return SFB_OK;
+  }
+
+  // ---------------------------------------------------------------- workspace
+  int Ld(int64_t L, int d) const {
+    int64_t f = 1;
+    for (int i = 0; i <= d; ++i) f *= cfg.factors[i];
+    return (int)(L / f);
+  }
+  void layout(int64_t B, int64_t L, int cfg_on, int64_t rows, WsLayout& w) const {
+    const int64_t Beff = cfg_on ? 2 * B : B;
+    const int MF = cfg.modulation_features, EF = cfg.embedding_features;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+    const int64_t R = std::max<int64_t>(rows, 1);
+    w.sigma = take(R * 4);
+    w.embrows = take(Beff * EF * 4);
+    w.tmp1 = take(Beff * EF * 4);
+    w.tmp2 = take(Beff * EF * 4);
+    w.fourier = take(R * 257 * 4);
+    w.h1 = take(R * MF * 4);
+    w.h2 = take(R * MF * 4);
+    w.feat = take(R * MF * 4);
+    w.ftable = take(R * (size_t)F_total * 4);
+    w.xbias = take(Beff * (size_t)std::max(XB_total, 1) * 4);
+    int ngn = 0;
+    for (int d = 0; d < cfg.depth; ++d) ngn += 4 * cfg.items[d] + 2;
+    w.stats_bytes = (size_t)ngn * Beff * 16 * sizeof(double);
+    w.stats = take(w.stats_bytes);
+    w.veff = take(Beff * L * 4);
+    w.xstate = take(B * L * 4);
+    for (int d = 0; d < cfg.depth; ++d) {
+      const size_t ld = Ld(L, d), C = cfg.channels[d];
+      w.ctx[d] = take((size_t)B * ld * cfg.context_channels[d] * sizeof(T));
+      w.bufA[d] = take((size_t)Beff * ld * C * 4);
+      w.T1[d] = take((size_t)Beff * ld * C * sizeof(T));
+      w.T2[d] = take((size_t)Beff * ld * C * sizeof(T));
+      if (cfg.attentions[d]) {
+        w.qkv[d] = take((size_t)Beff * ld * 1536 * sizeof(T));
+        w.o[d] = take((size_t)Beff * ld * 512 * sizeof(T));
+      } else {
+        w.qkv[d] = w.o[d] = 0;
+      }
+    }
+    w.total = off;
+  }
+  int workspace_bytes(int64_t B, int64_t L, int cfg_on, int64_t rows, size_t* out) override {
+    if (!finalized) return fail(SFB_ERR_STATE, "finalize first");
+    int64_t tf = 1;
+    for (int d = 0; d < cfg.depth; ++d) tf *= cfg.factors[d];
+    if (B <= 0 || L <= 0 || L % tf) return fail(SFB_ERR_INVALID, "L=%lld must be a positive multiple of %lld", (long long)L, (long long)tf);
+    if (L % 8) return fail(SFB_ERR_INVALID, "L must be a multiple of 8");
+    WsLayout w;
+    layout(B, L, cfg_on, rows, w);
+    *out = w.total + 1024;
+    return SFB_OK;
+  }
+
+  // ---------------------------------------------------------------- plan
+  uint8_t* wsb = nullptr;
+  template <typename U> U* at(size_t off) { return reinterpret_cast<U*>(wsb + off); }
+  int stats_next = 0;
+  double* new_stats(int Beff) { return at<double>(plan.lay.stats) + (size_t)(stats_next++) * Beff * 16; }
+
+  bool add_gemm(Op& op, const GemmW& g, const void* a1, int K1view, int L, int Beff, const void* a2, int B2) {
+    op.kind = OP_GEMM;
+    op.BN = pick_bn(g.N);
+    op.B = Beff; op.L = L; op.C = g.N;
+    GemmParams<T>& p = op.gp;
+    memset(&p, 0, sizeof p);
+    if (!fill_gemm_maps<T>(p, a1, K1view, L, Beff, a2, g.K2, B2, g.w, g.N, g.taps, op.BN)) return false;
+    p.bias = g.bias;
+    p.bias_mod = g.bias_mod;
+    p.gs = 1;
+    p.resid = op.resid;
+    p.out_r = op.out_r;
+    p.out_t = reinterpret_cast<T*>(op.out_t);
+    p.stats = op.stats_out;
+    return true;
+  }
+  void set_dbg(Op& op, int rows, int cols) {
+    if (op.out_r) { op.dbg_off = (uint8_t*)op.out_r - wsb; op.dbg_dtype = 0; op.dbg_bytes = (size_t)rows * cols * 4; }
+    else { op.dbg_off = (uint8_t*)op.out_t - wsb; op.dbg_dtype = 1; op.dbg_bytes = (size_t)rows * cols * sizeof(T); }
+    op.dbg_rows = rows; op.dbg_cols = cols;
+  }
+
+  // One [Resnet, Modulation, Inject, Attention?, CrossAttention?] group.  `cur` = stats of the tensor in bufA[d].
+  int build_item(int d, int s, int i, double*& cur, bool want_t, bool want_stats) {
+    const int64_t B = plan.B;
+    const int Beff = plan.cfg_on ? 2 * (int)B : (int)B;
+    const int C = cfg.channels[d], L = Ld(plan.L, d), gs = C / 8, ctx = cfg.context_channels[d];
+    const ItemW& I = dw[d].items[s][i];
+    float* A = at<float>(plan.lay.bufA[d]);
+    T* T1 = at<T>(plan.lay.T1[d]);
+    T* T2 = at<T>(plan.lay.T2[d]);
+    const float* xb = I.has_xattn ? at<float>(plan.lay.xbias) + I.xb_off : nullptr;
+    auto base = [&](int kind) { Op o; o.kind = kind; o.depth = d; o.stack = s; o.item = i; o.L = L; o.C = C; o.gs = gs; o.B = Beff; return o; };
+    const int rows = Beff * L;
+    {  // gn1 + SiLU
+      Op o = base(OP_GN); o.in = A; o.in_is_f32 = 1; o.stats_in = cur; o.w0 = I.gn1_g; o.w1 = I.gn1_b; o.out_t = T1;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    double* sB = new_stats(Beff);
+    if (d == 0) {
+      Op o = base(OP_CONV_C8); o.in = T1; o.w0 = I.c8_w1; o.w1 = I.c8_b1; o.out_t = T2; o.stats_out = sB;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    } else {
+      Op o = base(OP_GEMM); o.out_t = T2; o.stats_out = sB;
+      if (!add_gemm(o, I.conv1, T1, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (conv1 d%d)", d);
+      o.gp.gs = gs; set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    {  // gn2 + SiLU
+      Op o = base(OP_GN); o.in = T2; o.in_is_f32 = 0; o.stats_in = sB; o.w0 = I.gn2_g; o.w1 = I.gn2_b; o.out_t = T1;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    if (d == 0) {
+      Op o = base(OP_CONV_C8); o.in = T1; o.w0 = I.c8_w2; o.w1 = I.c8_b2; o.resid = A; o.out_r = A;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    } else {
+      Op o = base(OP_GEMM); o.resid = A; o.out_r = A;
+      if (!add_gemm(o, I.conv2, T1, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (conv2 d%d)", d);
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    {  // Modulation
+      Op o = base(OP_LN); o.in = A; o.out_t = T1; o.out_r = A; o.ft_off = I.mod_off;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    const bool last_is_inject = !I.has_attn;
+    double* sOut = want_stats ? new_stats(Beff) : nullptr;
+    if (d == 0) {
+      Op o = base(OP_INJ_C8); o.in = T1; o.resid = A; o.in2 = at<T>(plan.lay.ctx[d]); o.ctx = ctx; o.w0 = I.c8_wi; o.w1 = I.c8_bi;
+      o.w2 = xb; o.out_r = A; o.out_t = want_t ? T2 : nullptr; o.stats_out = sOut;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    } else {
+      Op o = base(OP_GEMM); o.resid = A; o.out_r = A;
+      o.out_t = (last_is_inject && want_t) ? T2 : nullptr;
+      o.stats_out = last_is_inject ? sOut : nullptr;
+      if (!add_gemm(o, I.inject, T1, C, L, Beff, at<T>(plan.lay.ctx[d]), (int)B)) return fail(SFB_ERR_CUDA, "tensor map encode failed (inject d%d)", d);
+      o.gp.gs = gs;
+      if (last_is_inject && xb) { o.gp.rowvec = xb; o.gp.rowvec_stride = XB_total; }
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    if (I.has_attn) {
+      T* QKV = at<T>(plan.lay.qkv[d]);
+      T* O = at<T>(plan.lay.o[d]);
+      {  // pre-norm (affine folded into W_qkv)
+        Op o = base(OP_LN); o.in = A; o.out_t = T1; o.out_r = nullptr; o.ft_off = -1;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+      {
+        Op o = base(OP_GEMM); o.out_t = QKV;
+        if (!add_gemm(o, I.qkv, T1, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (qkv d%d)", d);
+        set_dbg(o, rows, 1536); plan.ops.push_back(o);
+      }
+      {
+        Op o = base(OP_ATTN); o.in = QKV; o.out_t = O;
+        constexpr int AE = ElemTraits<T>::kAtomElems;
+        if (!make_tmap3<T>(&o.ap.tmQ, QKV, 1536, L, Beff, AE, 128) ||
+            !make_tmap3<T>(&o.ap.tmKV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV))
+          return fail(SFB_ERR_CUDA, "tensor map encode failed (attention d%d)", d);
+        o.ap.out = O; o.ap.n_tokens = L; o.ap.scale_log2 = 1.4426950408889634f / 8.0f;
+        set_dbg(o, rows, 512); plan.ops.push_back(o);
+      }
+      {
+        Op o = base(OP_GEMM); o.resid = A; o.out_r = A; o.out_t = want_t ? T2 : nullptr; o.stats_out = sOut;
+        if (!add_gemm(o, I.out, O, 512, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (to_out d%d)", d);
+        o.gp.gs = gs;
+        if (xb) { o.gp.rowvec = xb; o.gp.rowvec_stride = XB_total; }
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+    }
+    cur = sOut;
+    return SFB_OK;
+  }
+
+  int build_block(int d) {
+    const int64_t B = plan.B;
+    const int Beff = plan.cfg_on ? 2 * (int)B : (int)B;
+    const int C = cfg.channels[d], L = Ld(plan.L, d), f = cfg.factors[d];
+    const int D = cfg.depth;
+    const DepthW& W = dw[d];
+    float* A = at<float>(plan.lay.bufA[d]);
+    double* cur = new_stats(Beff);
+    if (d == 0) {
+      Op o; o.kind = OP_D0_DOWN; o.depth = 0; o.stack = 2; o.L = L; o.C = C; o.B = Beff; o.w0 = W.c8_dw; o.w1 = W.c8_db;
+      o.out_r = A; o.stats_out = cur; set_dbg(o, Beff * L, C); plan.ops.push_back(o);
+    } else {
+      const int Cin = cfg.channels[d - 1];
+      Op o; o.depth = d; o.stack = 2; o.out_r = A; o.stats_out = cur;
+      if (!add_gemm(o, W.down, at<T>(plan.lay.T2[d - 1]), f * Cin, L, Beff, nullptr, 0))
+        return fail(SFB_ERR_CUDA, "tensor map encode failed (down d%d)", d);
+      o.gp.gs = C / 8; set_dbg(o, Beff * L, C); plan.ops.push_back(o);
+    }
+    const int n = cfg.items[d];
+    const bool has_inner = d + 1 < D;
+    for (int i = 0; i < n; ++i) {
+      const bool last = i == n - 1;
+      int rc = build_item(d, 0, i, cur, /*want_t=*/last && has_inner, /*want_stats=*/!last || !has_inner);
+      if (rc) return rc;
+    }
+    if (has_inner) {
+      int rc = build_block(d + 1);   // leaves skip + s * up in bufA[d], stats in inner_out_stats
+      if (rc) return rc;
+      cur = inner_out_stats;
+    }
+    for (int i = 0; i < n; ++i) {
+      const bool last = i == n - 1;
+      int rc = build_item(d, 1, i, cur, /*want_t=*/last, /*want_stats=*/!last);
+      if (rc) return rc;
+    }
+    if (d == 0) {
+      Op o; o.kind = OP_D0_UP; o.depth = 0; o.stack = 2; o.L = L; o.C = C; o.B = Beff; o.in = at<T>(plan.lay.T2[0]);
+      o.w0 = W.c8_uw; o.fscalar = W.c8_ub; o.taps = W.up_taps; o.ft_off = W.skip_off; o.out_r = at<float>(plan.lay.veff);
+      set_dbg(o, Beff, L); plan.ops.push_back(o);
+    } else {
+      const int Cin = cfg.channels[d - 1];
+      float* Ap = at<float>(plan.lay.bufA[d - 1]);
+      double* so = new_stats(Beff);
+      Op o; o.depth = d; o.stack = 3; o.resid = Ap; o.out_r = Ap; o.stats_out = so; o.ft_off = W.skip_off;
+      if (!add_gemm(o, W.up, at<T>(plan.lay.T2[d]), C, L, Beff, nullptr, 0))
+        return fail(SFB_ERR_CUDA, "tensor map encode failed (up d%d)", d);
+      o.gp.gs = Cin / 8; set_dbg(o, Beff * Ld(plan.L, d - 1), Cin); plan.ops.push_back(o);
+      inner_out_stats = so;
+    }
+    return SFB_OK;
+  }
+  double* inner_out_stats = nullptr;
+
+  int ensure_plan(int64_t B, int64_t L, int cfg_on, int64_t rows, void* ws, size_t ws_bytes) {
+    if (!finalized) return fail(SFB_ERR_STATE, "finalize first");
+    size_t need = 0;
+    int rc = workspace_bytes(B, L, cfg_on, rows, &need);
+    if (rc) return rc;
+    if (!ws || ws_bytes < need) return fail(SFB_ERR_INVALID, "workspace too small: %zu < %zu", ws_bytes, need);
+    uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 1024));
+    WsLayout lay;
+    layout(B, L, cfg_on, rows, lay);
+    if (plan.ws == base && plan.B == B && plan.L == L && plan.cfg_on == cfg_on && plan.lay.total == lay.total &&
+        !plan.ops.empty())
+      return SFB_OK;
+    plan = Plan();
+    plan.B = B; plan.L = L; plan.cfg_on = cfg_on; plan.ws = base; plan.lay = lay;
+    wsb = base;
+    stats_next = 0;
+    rc = build_block(0);
+    if (rc) { plan.ops.clear(); return rc; }
+    return SFB_OK;
+  }
+  int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes) override {
+    int rc = ensure_plan(B, L, cfg_on, B, ws, ws_bytes);
+    if (rc) return rc;
+    return (int)plan.ops.size();
+  }
+  int op_info(int i, char* buf, int len) override {
+    if (i < 0 || i >= (int)plan.ops.size()) return fail(SFB_ERR_INVALID, "op index out of range");
+    const Op& o = plan.ops[i];
+    snprintf(buf, len, "%s %d %d %d %zu %zu %d %d %d", kOpNames[o.kind], o.depth, o.stack, o.item, o.dbg_off, o.dbg_bytes,
+             o.dbg_rows, o.dbg_cols, o.dbg_dtype);
+    return SFB_OK;
+  }
+
+  // ---------------------------------------------------------------- execution
+  struct StepCtx {
+    const float* frow;   // feature-table row(s)
+    int bstride, bmod;   // per-clip row stride (0: shared) and modulo
+    const float* x;      // [B, L] net input
+  };
+
+  template <int NV>
+  void launch_ln(const Op& o, const StepCtx& sc, cudaStream_t st) {
+    const size_t rows = (size_t)o.B * o.L;
+    const int lpr = (o.C / 8 < 32) ? o.C / 8 : 32, rpw = 32 / lpr;
+    const size_t warps = (rows + rpw - 1) / rpw;
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    const float* scale = o.ft_off >= 0 ? sc.frow + o.ft_off : nullptr;
+    const float* shift = o.ft_off >= 0 ? sc.frow + o.ft_off + o.C : nullptr;
+    ln_mod_kernel<T, NV><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(o.in), scale, shift, sc.bstride, sc.bmod,
+                                                reinterpret_cast<T*>(o.out_t), o.out_r, rows, o.L, o.C, 1e-5f);
+  }
+
+  int run_unet(const StepCtx& sc, cudaStream_t st) {
+    const int Bx = (int)plan.B;
+    SFB_CUDA(cudaMemsetAsync(at<double>(plan.lay.stats), 0, plan.lay.stats_bytes, st));
+    ++launches;
+    int n = (int)plan.ops.size();
+    if (op_limit >= 0 && op_limit < n) n = op_limit;
+    for (int i = 0; i < n; ++i) {
+      const Op& o = plan.ops[i];
+      const unsigned lb = (unsigned)((o.L + 255) / 256);
+      switch (o.kind) {
+        case OP_D0_DOWN:
+          d0_down_kernel<<<dim3(lb, o.B), 256, 0, st>>>(sc.x, o.w0, o.w1, o.out_r, o.stats_out, o.L, Bx);
+          break;
+        case OP_GN: {
+          const size_t nvec = (size_t)o.L * o.C / 8;
+          unsigned bpc = (unsigned)std::min<size_t>(std::max<size_t>((nvec + 2047) / 2048, 1), 2048);
+          const size_t sm = (size_t)2 * o.C * sizeof(float);
+          if (o.in_is_f32)
+            gn_apply_silu_kernel<float, T><<<dim3(bpc, o.B), 256, sm, st>>>(reinterpret_cast<const float*>(o.in), o.stats_in, o.w0, o.w1,
+                                                                          reinterpret_cast<T*>(o.out_t), o.L, o.C, o.gs, 1e-5f);
+          else
+            gn_apply_silu_kernel<T, T><<<dim3(bpc, o.B), 256, sm, st>>>(reinterpret_cast<const T*>(o.in), o.stats_in, o.w0, o.w1,
+                                                                      reinterpret_cast<T*>(o.out_t), o.L, o.C, o.gs, 1e-5f);
+          break;
+        }
+        case OP_CONV_C8:
+          conv3_c8_kernel<T><<<dim3(lb, o.B), 256, 0, st>>>(reinterpret_cast<const T*>(o.in), o.w0, o.w1, o.resid, o.out_r,
+                                                            reinterpret_cast<T*>(o.out_t), o.stats_out, o.L);
+          break;
+        case OP_INJ_C8:
+          inject_c8_kernel<T, 2><<<dim3(lb, o.B), 256, 0, st>>>(reinterpret_cast<const T*>(o.in), o.resid,
+                                                               reinterpret_cast<const T*>(o.in2), o.w0, o.w1, o.w2, o.out_r,
+                                                               reinterpret_cast<T*>(o.out_t), o.stats_out, o.L, Bx);
+          break;
+        case OP_D0_UP:
+          d0_up_kernel<T><<<dim3(lb, o.B), 256, 0, st>>>(reinterpret_cast<const T*>(o.in), o.w0, o.fscalar, sc.frow + o.ft_off,
+                                                        sc.bstride, sc.bmod, sc.x, o.out_r, o.L, Bx, o.taps);
+          break;
+        case OP_GEMM: {
+          if (o.ft_off >= 0) {
+            GemmParams<T> p = o.gp;
+            p.colscale = sc.frow + o.ft_off;
+            p.cs_bstride = sc.bstride;
+            p.cs_bmod = sc.bmod;
+            launch_gemm<T>(p, o.BN, o.B, st);
+          } else {
+            launch_gemm<T>(o.gp, o.BN, o.B, st);
+          }
+          break;
+        }
+        case OP_LN: {
+          const int lpr = (o.C / 8 < 32) ? o.C / 8 : 32;
+          const int nv = o.C / (8 * lpr);
+          if (nv == 1) launch_ln<1>(o, sc, st);
+          else if (nv == 2) launch_ln<2>(o, sc, st);
+          else launch_ln<4>(o, sc, st);
+          break;
+        }
+        case OP_ATTN: {
+          dim3 grid((o.L + 127) / 128, 8, o.B);
+          attn_tc_kernel<T><<<grid, kAttnThreads, attn_smem_bytes<T>(), st>>>(o.ap);
+          break;
+        }
+      }
+      ++launches;
+    }
+    SFB_CUDA(cudaGetLastError());
+    return SFB_OK;
+  }
+
+  // loop-invariant conditioning: time features -> modulation / skip tables; cross-attention biases; onset pyramid layout
+  int prepare(const float* sigma_dev, int rows, const float* const* channels, int n_channels, const float* embedding,
+              int64_t M, cudaStream_t st) {
+    const int64_t B = plan.B, L = plan.L;
+    const int Beff = plan.cfg_on ? 2 * (int)B : (int)B;
+    const int MF = cfg.modulation_features, EF = cfg.embedding_features;
+    if (M != 1) return fail(SFB_ERR_UNSUPPORTED, "embedding length M=%lld: only the M_ctx = 1 path is implemented (embedding_max_length: 1)", (long long)M);
+    if (n_channels < cfg.depth) return fail(SFB_ERR_INVALID, "channels: need %d context tensors, got %d", cfg.depth, n_channels);
+    if (!embedding) return fail(SFB_ERR_INVALID, "embedding is required (ClassifierFreeGuidancePlugin)");
+    const WsLayout& w = plan.lay;
+    auto lin = [&](const float* in, const float* W, const float* bias, float* out, int r, int K, int J, int ldo, int ai, int ao) {
+      const unsigned blocks = (unsigned)((J + 7) / 8);
+      linear_act_kernel<<<blocks, 256, 0, st>>>(in, W, bias, out, r, K, J, K, ldo, ai, ao);
+      ++launches;
+    };
+    // time features (A.3)
+    fourier_embed_kernel<<<rows, 128, 0, st>>>(sigma_dev, t_w, at<float>(w.fourier), rows, 128);
+    ++launches;
+    lin(at<float>(w.fourier), t_lw, t_lb, at<float>(w.h1), rows, 257, MF, MF, ACT_NONE, ACT_GELU);
+    lin(at<float>(w.h1), t_mw, t_mb, at<float>(w.h2), rows, MF, MF, MF, ACT_NONE, ACT_GELU);
+    lin(at<float>(w.h2), t_mw, t_mb, at<float>(w.feat), rows, MF, MF, MF, ACT_NONE, ACT_GELU);
+    lin(at<float>(w.feat), ft_w, ft_b, at<float>(w.ftable), rows, MF, F_total, F_total, ACT_SILU, ACT_NONE);
+    // cross-attention biases (A.4 + A.7, M_ctx = 1)
+    build_emb_rows_kernel<<<Beff, 128, 0, st>>>(embedding, fixed_emb, at<float>(w.embrows), (int)B, Beff, EF);
+    ++launches;
+    for (int d = 0; d < cfg.depth; ++d)
+      for (int s = 0; s < 2; ++s)
+        for (const ItemW& I : dw[d].items[s]) {
+          if (!I.has_xattn) continue;
+          ln_rows_kernel<<<(Beff + 7) / 8, 256, 0, st>>>(at<float>(w.embrows), I.x_ng, I.x_nb, at<float>(w.tmp1), Beff, EF, 1e-5f);
+          ++launches;
+          lin(at<float>(w.tmp1), I.x_wv, nullptr, at<float>(w.tmp2), Beff, EF, 512, 512, ACT_NONE, ACT_NONE);
+          lin(at<float>(w.tmp2), I.x_wo, nullptr, at<float>(w.xbias) + I.xb_off, Beff, 512, cfg.channels[d], XB_total, ACT_NONE, ACT_NONE);
+        }
+    // onset pyramid NCL f32 -> NLC operand precision
+    for (int d = 0; d < cfg.depth; ++d) {
+      const int ld = Ld(L, d);
+      if (!channels[d]) return fail(SFB_ERR_INVALID, "channels[%d] is null", d);
+      ncl_to_nlc_kernel<T><<<dim3((ld + 255) / 256, (unsigned)B), 256, 0, st>>>(channels[d], at<T>(w.ctx[d]), cfg.context_channels[d], ld);
+      ++launches;
+    }
+    SFB_CUDA(cudaGetLastError());
+    return SFB_OK;
+  }
+
+  int unet_forward(const float* x, const float* sigma, const float* const* channels, int n_channels, const float* embedding,
+                   int64_t M, float scale, float* v_out, int64_t B, int64_t L, void* ws, size_t ws_bytes,
+                   cudaStream_t st) override {
+    const int cfg_on = scale != 1.0f;
+    int rc = ensure_plan(B, L, cfg_on, B, ws, ws_bytes);
+    if (rc) return rc;
+    wsb = reinterpret_cast<uint8_t*>(plan.ws);
+    launches = 0;
+    rc = prepare(sigma, (int)B, channels, n_channels, embedding, M, st);
+    if (rc) return rc;
+    StepCtx sc{at<float>(plan.lay.ftable), F_total, (int)B, x};
+    rc = run_unet(sc, st);
+    if (rc) return rc;
+    const size_t n = (size_t)B * L;
+    cfg_combine_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(at<float>(plan.lay.veff), v_out, n, cfg_on, scale);
+    ++launches;
+    SFB_CUDA(cudaGetLastError());
+    return SFB_OK;
+  }
+
+  int sample(const float* x_noisy, int num_steps, const float* const* channels, int n_channels, const float* embedding,
+             int64_t M, float scale, float* x_out, float* traj_x, float* traj_v, const float* teacher_x, int64_t B, int64_t L,
+             void* ws, size_t ws_bytes, cudaStream_t st) override {
+    if (num_steps <= 0) return fail(SFB_ERR_INVALID, "num_steps must be positive");
+    const int cfg_on = scale != 1.0f;
+    int rc = ensure_plan(B, L, cfg_on, num_steps + 1, ws, ws_bytes);
+    if (rc) return rc;
+    wsb = reinterpret_cast<uint8_t*>(plan.ws);
+    launches = 0;
+    // LinearSchedule (A.2): torch.linspace(1, 0, N + 1) in fp32, same two-sided formula as ATen.
+    std::vector<float> sig(num_steps + 1);   // host copy for the per-step alpha / beta scalars
+    {
+      const int steps = num_steps + 1;
+      const float start = 1.f, end = 0.f;
+      const float step = (end - start) / (float)(steps - 1);
+      const int half = steps / 2;
+      for (int i = 0; i < steps; ++i) sig[i] = i < half ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+    }
+    sigma_linspace_kernel<<<(num_steps + 256) / 256, 256, 0, st>>>(at<float>(plan.lay.sigma), num_steps + 1);
+    ++launches;
+    rc = prepare(at<float>(plan.lay.sigma), num_steps + 1, channels, n_channels, embedding, M, st);
+    if (rc) return rc;
+    const size_t n = (size_t)B * L;
+    float* xs = at<float>(plan.lay.xstate);
+    SFB_CUDA(cudaMemcpyAsync(xs, x_noisy, n * 4, cudaMemcpyDeviceToDevice, st));
+    const float hp = 1.5707963267948966f;
+    for (int i = 0; i < num_steps; ++i) {
+      const float* xe = teacher_x ? teacher_x + (size_t)i * n : xs;
+      StepCtx sc{at<float>(plan.lay.ftable) + (size_t)i * F_total, 0, 1, xe};
+      rc = run_unet(sc, st);
+      if (rc) return rc;
+      const float a = cosf(sig[i] * hp), b = sinf(sig[i] * hp), a2 = cosf(sig[i + 1] * hp), b2 = sinf(sig[i + 1] * hp);
+      sampler_update_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(
+          xe, at<float>(plan.lay.veff), xs, traj_x ? traj_x + (size_t)i * n : nullptr, traj_v ? traj_v + (size_t)i * n : nullptr,
+          n, cfg_on, scale, a, b, a2, b2);
+      ++launches;
+    }
+    SFB_CUDA(cudaMemcpyAsync(x_out, xs, n * 4, cudaMemcpyDeviceToDevice, st));
+    SFB_CUDA(cudaGetLastError());
+    return SFB_OK;
+  }
+};
+
+}  // namespace
+
+// ================================================================================================== C ABI
+struct sfb_handle {
+  std::unique_ptr<EngineBase> e;
+};
+
+template <typename T>
+static int dbg_gemm_t(const void* a1, const void* a2, const void* w, const float* bias, const float* resid, float* out_r,
+                      void* out_t, double* stats, int B, int L, int K1, int K2, int N, int taps, int a2_bmod, int bias_mod,
+                      int gs, cudaStream_t st) {
+  if (set_kernel_attrs<T>() != cudaSuccess) return SFB_ERR_CUDA;
+  const int BN = pick_bn(N);
+  if (!BN) return SFB_ERR_UNSUPPORTED;
+  GemmParams<T> p;
+  memset(&p, 0, sizeof p);
+  if (!fill_gemm_maps<T>(p, a1, K1, L, B, a2, K2, a2_bmod, w, N, taps, BN)) return SFB_ERR_CUDA;
+  p.bias = bias; p.bias_mod = bias_mod > 0 ? bias_mod : N; p.gs = gs > 0 ? gs : 1;
+  p.resid = resid; p.out_r = out_r; p.out_t = reinterpret_cast<T*>(out_t); p.stats = stats;
+  launch_gemm<T>(p, BN, B, st);
+  return cudaGetLastError() == cudaSuccess ? SFB_OK : SFB_ERR_CUDA;
+}
+template <typename T>
+static int dbg_attn_t(const void* qkv, void* out, int B, int N, cudaStream_t st) {
+  if (set_kernel_attrs<T>() != cudaSuccess) return SFB_ERR_CUDA;
+  AttnParams<T> p;
+  memset(&p, 0, sizeof p);
+  constexpr int AE = ElemTraits<T>::kAtomElems;
+  if (!make_tmap3<T>(&p.tmQ, qkv, 1536, N, B, AE, 128) || !make_tmap3<T>(&p.tmKV, qkv, 1536, N, B, AE, AttnCfg<T>::BKV))
+    return SFB_ERR_CUDA;
+  p.out = reinterpret_cast<T*>(out); p.n_tokens = N; p.scale_log2 = 1.4426950408889634f / 8.0f;
+  attn_tc_kernel<T><<<dim3((N + 127) / 128, 8, B), kAttnThreads, attn_smem_bytes<T>(), st>>>(p);
+  return cudaGetLastError() == cudaSuccess ? SFB_OK : SFB_ERR_CUDA;
+}
+extern "C" {
+
+int sfb_create(const sfb_unet_config* cfg, int device, sfb_handle** out) {
+  if (!cfg || !out) return SFB_ERR_INVALID;
+  if (cfg->depth < 2 || cfg->depth > SFB_MAX_DEPTH) return SFB_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SFB_ERR_CUDA;   // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return SFB_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SFB_ERR_CUDA;
+  if (prop.major != 10) return SFB_ERR_UNSUPPORTED;   // tcgen05 / TMEM kernels are sm_100a only
+  sfb_handle* h = new sfb_handle();
+  if (cfg->precision == SFB_PRECISION_BF16) h->e.reset(new Engine<__nv_bfloat16>());
+  else h->e.reset(new Engine<float>());
+  h->e->cfg = *cfg;
+  h->e->device = device;
+  *out = h;
+  return SFB_OK;
+}
+
+void sfb_destroy(sfb_handle* h) { delete h; }
+
+const char* sfb_last_error(const sfb_handle* h) { return h ? h->e->err.c_str() : "null handle"; }
+
+int sfb_set_param(sfb_handle* h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim) {
+  if (!h || !name || !data || !shape || ndim < 0 || ndim > 4) return SFB_ERR_INVALID;
+  if (dtype != SFB_DTYPE_F32) return h->e->fail(SFB_ERR_INVALID, "only f32 parameters are accepted");
+  if (h->e->finalized) return h->e->fail(SFB_ERR_STATE, "already finalized");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.v.resize(n);
+  cudaError_t e = cudaMemcpy(t.v.data(), data, n * sizeof(float), cudaMemcpyDefault);
+  if (e != cudaSuccess) return h->e->fail(SFB_ERR_CUDA, "set_param(%s): %s", name, cudaGetErrorString(e));
+  h->e->params[name] = std::move(t);
+  return SFB_OK;
+}
+
+int sfb_finalize(sfb_handle* h) {
+  if (!h) return SFB_ERR_INVALID;
+  if (h->e->finalized) return SFB_OK;
+  cudaSetDevice(h->e->device);
+  return h->e->finalize();
+}
+
+int sfb_workspace_bytes(sfb_handle* h, int64_t B, int64_t L, int cfg_on, int64_t rows, size_t* out) {
+  if (!h || !out) return SFB_ERR_INVALID;
+  return h->e->workspace_bytes(B, L, cfg_on, rows, out);
+}
+
+int sfb_unet_forward(sfb_handle* h, const float* x, const float* sigma, const float* const* channels, int n_channels,
+                     const float* embedding, int64_t M, float embedding_scale, float* v_out, int64_t B, int64_t L,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return SFB_ERR_INVALID;
+  if (!x || !sigma || !channels || !v_out) return h->e->fail(SFB_ERR_INVALID, "null argument");
+  return h->e->unet_forward(x, sigma, channels, n_channels, embedding, M, embedding_scale, v_out, B, L, workspace,
+                            workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int sfb_sample(sfb_handle* h, const float* x_noisy, int num_steps, const float* const* channels, int n_channels,
+               const float* embedding, int64_t M, float embedding_scale, float* x_out, float* traj_x, float* traj_v,
+               const float* teacher_x, int64_t B, int64_t L, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return SFB_ERR_INVALID;
+  if (!x_noisy || !channels || !x_out) return h->e->fail(SFB_ERR_INVALID, "null argument");
+  return h->e->sample(x_noisy, num_steps, channels, n_channels, embedding, M, embedding_scale, x_out, traj_x, traj_v,
+                      teacher_x, B, L, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int64_t sfb_last_launch_count(const sfb_handle* h) { return h ? h->e->launches : 0; }
+
+int sfb_dbg_set_op_limit(sfb_handle* h, int n_ops) {
+  if (!h) return SFB_ERR_INVALID;
+  h->e->op_limit = n_ops;
+  return SFB_OK;
+}
+int sfb_dbg_plan_size(sfb_handle* h, int64_t B, int64_t L, int cfg_on, void* workspace, size_t workspace_bytes) {
+  if (!h) return SFB_ERR_INVALID;
+  return h->e->plan_size(B, L, cfg_on, workspace, workspace_bytes);
+}
+int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len) {
+  if (!h || !buf) return SFB_ERR_INVALID;
+  return h->e->op_info(i, buf, buf_len);
+}
+
+int sfb_dbg_gemm(int bf16, const void* a1, const void* a2, const void* w, const float* bias, const float* resid,
+                 float* out_r, void* out_t, double* stats, int B, int L, int K1, int K2, int N, int taps, int a2_bmod,
+                 int bias_mod, int gs, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bf16) return dbg_gemm_t<__nv_bfloat16>(a1, a2, w, bias, resid, out_r, out_t, stats, B, L, K1, K2, N, taps, a2_bmod, bias_mod, gs, st);
+  return dbg_gemm_t<float>(a1, a2, w, bias, resid, out_r, out_t, stats, B, L, K1, K2, N, taps, a2_bmod, bias_mod, gs, st);
+}
+
+int sfb_dbg_attention(int bf16, const void* qkv, void* out, int B, int N, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return bf16 ? dbg_attn_t<__nv_bfloat16>(qkv, out, B, N, st) : dbg_attn_t<float>(qkv, out, B, N, st);
+}
+
+}  // extern "C"
