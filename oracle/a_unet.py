@@ -305,6 +305,8 @@ def stress_init_(net: UNetV0, seed: int = 7) -> UNetV0:
             p.copy_((torch.rand(p.shape, generator=g) - 0.5) * 0.5)
         elif name.endswith(("to_q.weight", "to_kv.weight")):
             p.mul_(4.0)
+        elif name.endswith("skip.bias"):
+            p.add_(1.0)        # skip scale ~ 1 so that deep-level errors are not attenuated on the way up
         elif ".skip." in name or ".mod.linear" in name:
             p.mul_(2.0)
     return net

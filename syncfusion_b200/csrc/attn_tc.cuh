@@ -17,6 +17,7 @@ template <typename T>
 struct AttnParams {
   CUtensorMap tmQ;    // qkv viewed [1536, N, B], box [atom, 128, 1]
   CUtensorMap tmKV;   // same tensor, box [atom, BKV, 1]
+  CUtensorMap tmV;    // same box; bf16: identical to tmKV, tf32: 128B swizzle with 32-byte atoms (MN-major tf32)
   T* out;             // [B, N, 512]
   int n_tokens;
   float scale_log2;   // log2(e) / sqrt(64)
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmKV);
+    tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
       uint8_t* sk = sKV + s * 2 * kKBytes;
       for (int a = 0; a < DA; ++a) {
         tma_load_3d(sk + a * BKV * 128, &p.tmKV, &kv_full[s], 512 + h * kHeadDim + a * AE, j * BKV, b);
-        tma_load_3d(sk + kKBytes + a * BKV * 128, &p.tmKV, &kv_full[s], 1024 + h * kHeadDim + a * AE, j * BKV, b);
+        tma_load_3d(sk + kKBytes + a * BKV * 128, &p.tmV, &kv_full[s], 1024 + h * kHeadDim + a * AE, j * BKV, b);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -122,7 +124,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
         const uint64_t da = make_smem_desc_sw128(ap + atom * 128 * 128 + within * 32, 16, 1024);
         // MN-major B: rows of the tile are keys (the MMA K dim) at 128-byte pitch; 8-key groups 1024 bytes apart
         // (SBO); head-dim atoms BKV*128 bytes apart (LBO, only used by the two-atom tf32 layout).
-        const uint64_t db = make_smem_desc_sw128(av + k * UK * 128, BKV * 128, 1024);
+        // bf16: SWIZZLE_128B, 8-key groups; tf32: SWIZZLE_128B_BASE32B, 4-key groups 512 bytes apart.
+        const uint64_t db = (sizeof(T) == 2) ? make_smem_desc(av + k * UK * 128, BKV * 128, 1024, 2)
+                                             : make_smem_desc(av + k * UK * 128, BKV * 128, 512, 1);
         umma_ss<TR::kTF32>(tmem_O, da, db, idesc_o, k != 0);
       }
     };

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) conv3_c8_kernel(const T* __restrict__ in,
       for (int j = 0; j < 8; ++j) acc[j] += rv[j];
     }
     if (out_r) Vec8<float>::store(out_r + g, acc);
-    if (out_t) Vec8<T>::store(out_t + g, acc);
+    if (out_t) store_operand8<T>(out_t + g, acc);
   }
   if (stats) stats8_block_reduce(acc, valid, stats + (size_t)b * 16, s_red);
 }
@@ -100,7 +100,7 @@ template <typename T, int CTX>
 __global__ void __launch_bounds__(256) inject_c8_kernel(const T* __restrict__ m_t, const float* m_r, const T* __restrict__ ctx,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         const float* __restrict__ xbias, float* out_r, T* __restrict__ out_t,
-                                                        double* __restrict__ stats, int L, int Bc) {
+                                                        double* __restrict__ stats, int L, int Bc, int xb_stride) {
   __shared__ float s_w[(8 + CTX) * 8];
   __shared__ float s_red[16];
   for (int i = threadIdx.x; i < (8 + CTX) * 8; i += blockDim.x) s_w[i] = w[i];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) inject_c8_kernel(const T* __restrict__ m_
     Vec8<T>::load(m_t + g, xv);
     Vec8<float>::load(m_r + g, rv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = __ldg(&bias[j]) + rv[j] + (xbias ? __ldg(&xbias[b * 8 + j]) : 0.f);
+    for (int j = 0; j < 8; ++j) acc[j] = __ldg(&bias[j]) + rv[j] + (xbias ? __ldg(&xbias[(size_t)b * xb_stride + j]) : 0.f);
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci)
 #pragma unroll
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) inject_c8_kernel(const T* __restrict__ m_
       for (int j = 0; j < 8; ++j) acc[j] += cv * s_w[(8 + ci) * 8 + j];
     }
     if (out_r) Vec8<float>::store(out_r + g, acc);
-    if (out_t) Vec8<T>::store(out_t + g, acc);
+    if (out_t) store_operand8<T>(out_t + g, acc);
   }
   if (stats) stats8_block_reduce(acc, valid, stats + (size_t)b * 16, s_red);
 }

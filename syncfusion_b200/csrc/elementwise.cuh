@@ -41,6 +41,19 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 
+// operand-precision store: bf16 rounds in the pack; fp32-mode operands are pre-rounded to tf32 (see from_f32<float>)
+template <typename T>
+__device__ __forceinline__ void store_operand8(T* p, const float* v) {
+  if constexpr (sizeof(T) == 4) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = from_f32<float>(v[j]);
+    Vec8<float>::store(p, r);
+  } else {
+    Vec8<T>::store(p, v);
+  }
+}
+
 __device__ __forceinline__ float silu_f(float y) { return y / (1.f + __expf(-y)); }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm + SiLU
@@ -74,7 +87,7 @@ __global__ void __launch_bounds__(256) gn_apply_silu_kernel(const Tin* __restric
     Vec8<Tin>::load(src + i * 8, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j] * s_ab[c0 + j] + s_ab[C + c0 + j]);
-    Vec8<Tout>::store(dst + i * 8, v);
+    store_operand8<Tout>(dst + i * 8, v);
   }
 }
 
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* in, const floa
       if (sc) t = t * (1.f + __ldg(&sc[c0 + j])) + __ldg(&sh[c0 + j]);
       y[j] = t;
     }
-    if (out_t) Vec8<Tout>::store(out_t + row * C + c0, y);
+    if (out_t) store_operand8<Tout>(out_t + row * C + c0, y);
     if (out_r) Vec8<float>::store(out_r + row * C + c0, y);
   }
 }

@@ -145,9 +145,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- descriptors ---------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit): [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
 // [61,64) layout (2 = SWIZZLE_128B).
-__host__ __device__ constexpr uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks; the only MN-major tf32 layout)
+__host__ __device__ constexpr uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   return (uint64_t((smem_addr >> 4) & 0x3FFF)) | (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+         (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32) | (uint64_t(1) << 46) | (uint64_t(layout) << 61);
+}
+__host__ __device__ constexpr uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2);
 }
 // Instruction descriptor (32 bit): [4,6) D fmt (1 = f32), [7,10) A fmt, [10,13) B fmt (0 f16, 1 bf16, 2 tf32),
 // [15] A major, [16] B major (0 = K-major, 1 = MN-major), [17,23) N>>3, [24,29) M>>4.
@@ -172,7 +176,13 @@ template <> struct ElemTraits<float> {
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
-template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+// fp32-mode operands feed kind::tf32 MMAs, which truncate the low 13 mantissa bits: round to nearest here so the
+// operand error is unbiased (half an ulp of tf32) instead of a systematic truncation.
+template <> __device__ __forceinline__ float from_f32<float>(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 }  // namespace sfb

@@ -52,7 +52,8 @@ template <> CUtensorMapDataType tmap_dtype<float>() { return CU_TENSOR_MAP_DATA_
 
 // rank-3 map over a contiguous [d2][d1][d0] tensor (d0 innermost), 128B swizzle, zero OOB fill.
 template <typename T>
-bool make_tmap3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+bool make_tmap3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -60,7 +61,7 @@ bool make_tmap3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t es[3] = {1, 1, 1};
   return fn(m, tmap_dtype<T>(), 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 template <typename T>
 bool make_tmap2(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint32_t b0, uint32_t b1) {
@@ -75,7 +76,13 @@ bool make_tmap2(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint
 }
 
 template <typename T> T host_cvt(float v);
-template <> float host_cvt<float>(float v) { return v; }
+template <> float host_cvt<float>(float v) {   // round-to-nearest tf32 (10-bit mantissa), matching cvt.rna.tf32.f32
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7F800000u) != 0x7F800000u) u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
 template <> __nv_bfloat16 host_cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -673,7 +680,9 @@ struct Engine : EngineBase {
         Op o = base(OP_ATTN); o.in = QKV; o.out_t = O;
         constexpr int AE = ElemTraits<T>::kAtomElems;
         if (!make_tmap3<T>(&o.ap.tmQ, QKV, 1536, L, Beff, AE, 128) ||
-            !make_tmap3<T>(&o.ap.tmKV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV))
+            !make_tmap3<T>(&o.ap.tmKV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV) ||
+            !make_tmap3<T>(&o.ap.tmV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV,
+                           sizeof(T) == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
           return fail(SFB_ERR_CUDA, "tensor map encode failed (attention d%d)", d);
         o.ap.out = O; o.ap.n_tokens = L; o.ap.scale_log2 = 1.4426950408889634f / 8.0f;
         set_dbg(o, rows, 512); plan.ops.push_back(o);
@@ -827,7 +836,7 @@ struct Engine : EngineBase {
         case OP_INJ_C8:
           inject_c8_kernel<T, 2><<<dim3(lb, o.B), 256, 0, st>>>(reinterpret_cast<const T*>(o.in), o.resid,
                                                                reinterpret_cast<const T*>(o.in2), o.w0, o.w1, o.w2, o.out_r,
-                                                               reinterpret_cast<T*>(o.out_t), o.stats_out, o.L, Bx);
+                                                               reinterpret_cast<T*>(o.out_t), o.stats_out, o.L, Bx, XB_total);
           break;
         case OP_D0_UP:
           d0_up_kernel<T><<<dim3(lb, o.B), 256, 0, st>>>(reinterpret_cast<const T*>(o.in), o.w0, o.fscalar, sc.frow + o.ft_off,
@@ -1001,7 +1010,9 @@ static int dbg_attn_t(const void* qkv, void* out, int B, int N, cudaStream_t st)
   AttnParams<T> p;
   memset(&p, 0, sizeof p);
   constexpr int AE = ElemTraits<T>::kAtomElems;
-  if (!make_tmap3<T>(&p.tmQ, qkv, 1536, N, B, AE, 128) || !make_tmap3<T>(&p.tmKV, qkv, 1536, N, B, AE, AttnCfg<T>::BKV))
+  if (!make_tmap3<T>(&p.tmQ, qkv, 1536, N, B, AE, 128) || !make_tmap3<T>(&p.tmKV, qkv, 1536, N, B, AE, AttnCfg<T>::BKV) ||
+      !make_tmap3<T>(&p.tmV, qkv, 1536, N, B, AE, AttnCfg<T>::BKV,
+                     sizeof(T) == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
     return SFB_ERR_CUDA;
   p.out = reinterpret_cast<T*>(out); p.n_tokens = N; p.scale_log2 = 1.4426950408889634f / 8.0f;
   attn_tc_kernel<T><<<dim3((N + 127) / 128, 8, B), kAttnThreads, attn_smem_bytes<T>(), st>>>(p);
