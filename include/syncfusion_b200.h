@@ -102,6 +102,11 @@ int sfb_dbg_set_op_limit(sfb_handle* h, int n_ops);
  * "kind depth stack item out_offset out_bytes rows cols dtype". */
 int sfb_dbg_plan_size(sfb_handle* h, int64_t B, int64_t L, int cfg_on, void* workspace, size_t workspace_bytes);
 int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len);
+/* Per-op device timing: when enabled, every launch of a U-Net evaluation is bracketed by CUDA events on the caller's
+ * stream; after the caller synchronises, the report holds one line per plan op of the most recent evaluation:
+ * "index kind depth stack item ms flops bytes" (algorithmic flops / bytes).  bench.py's roofline comes from this. */
+int sfb_dbg_profile(sfb_handle* h, int enable);
+int sfb_dbg_profile_report(sfb_handle* h, char* buf, int buf_len);
 /* Stand-alone kernels on raw device buffers (unit tests):
  *   gemm: out = resid + (A1 (*) W + A2 W2 + bias), A* [B, L, K*] in operand precision (bf16 or f32 per `bf16`),
  *         W [taps*N, K1+K2] same precision, out_r f32 / out_t operand precision (nullable), stats f64 [B,8,2]. */

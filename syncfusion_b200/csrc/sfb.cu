@@ -132,6 +132,8 @@ struct EngineBase {
                      const float* teacher_x, int64_t B, int64_t L, void* ws, size_t ws_bytes, cudaStream_t st) = 0;
   virtual int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes) = 0;
   virtual int op_info(int i, char* buf, int len) = 0;
+  virtual int profile_report(char* buf, int len) = 0;
+  bool profiling = false;
   int fail(int code, const char* fmt, ...) {
     char b[512];
     va_list ap;
@@ -229,7 +231,7 @@ struct Engine : EngineBase {
     double* stats_out = nullptr;
     const float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
     float fscalar = 0.f;
-    int L = 0, C = 0, gs = 0, B = 0, taps = 1, in_is_f32 = 0, ctx = 0;
+    int L = 0, C = 0, gs = 0, B = 0, taps = 1, in_is_f32 = 0, ctx = 0, k2 = 0;
     int ft_off = -1;      // feature-table column offset (Modulation scale | SkipModulate scale), -1: none
     GemmParams<T> gp;
     AttnParams<T> ap;
@@ -252,6 +254,7 @@ struct Engine : EngineBase {
 
   ~Engine() override {
     for (void* p : owned) cudaFree(p);
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
   }
 
   // ---------------------------------------------------------------- parameter access
@@ -589,7 +592,7 @@ struct Engine : EngineBase {
   bool add_gemm(Op& op, const GemmW& g, const void* a1, int K1view, int L, int Beff, const void* a2, int B2) {
     op.kind = OP_GEMM;
     op.BN = pick_bn(g.N);
-    op.B = Beff; op.L = L; op.C = g.N;
+    op.B = Beff; op.L = L; op.C = g.N; op.k2 = g.K2;
     GemmParams<T>& p = op.gp;
     memset(&p, 0, sizeof p);
     if (!fill_gemm_maps<T>(p, a1, K1view, L, Beff, a2, g.K2, B2, g.w, g.N, g.taps, op.BN)) return false;
@@ -751,6 +754,51 @@ struct Engine : EngineBase {
     return SFB_OK;
   }
   double* inner_out_stats = nullptr;
+  std::vector<cudaEvent_t> prof_ev;   // 2 per op: events around every launch of the most recent U-Net evaluation
+
+  // One line per plan op: "index kind depth stack item ms flops bytes" (algorithmic flops / bytes of the op).
+  int profile_report(char* buf, int len) override {
+    if (prof_ev.size() < 2 * plan.ops.size()) return fail(SFB_ERR_STATE, "no profiled evaluation recorded");
+    std::string out;
+    char line[160];
+    for (size_t i = 0; i < plan.ops.size(); ++i) {
+      const Op& o = plan.ops[i];
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, prof_ev[2 * i], prof_ev[2 * i + 1]) != cudaSuccess) ms = -1.f;
+      double flops = 0, bytes = 0;
+      const double rows = (double)o.B * o.L;
+      if (o.kind == OP_GEMM) {
+        const double K = (double)o.gp.taps * o.gp.K1 + (o.gp.k2_chunks ? (double)(o.k2) : 0.0);
+        flops = 2.0 * rows * o.gp.N * K;
+        bytes = rows * K / o.gp.taps * sizeof(T) + rows * o.gp.N * ((o.gp.resid ? 4 : 0) + (o.gp.out_r ? 4 : 0) + (o.gp.out_t ? sizeof(T) : 0)) +
+                (double)o.gp.taps * o.gp.N * (K / o.gp.taps) * sizeof(T);
+      } else if (o.kind == OP_ATTN) {
+        flops = 4.0 * (double)o.B * 8 * (double)o.L * o.L * 64;
+        bytes = rows * (1536 + 512) * sizeof(T);
+      } else if (o.kind == OP_GN) {
+        bytes = rows * o.C * ((o.in_is_f32 ? 4 : sizeof(T)) + sizeof(T));
+      } else if (o.kind == OP_LN) {
+        bytes = rows * o.C * (4 + sizeof(T) + (o.out_r ? 4 : 0));
+      } else if (o.kind == OP_CONV_C8) {
+        flops = 2.0 * rows * 8 * 24;
+        bytes = rows * 8 * (sizeof(T) + (o.resid ? 4 : 0) + (o.out_r ? 4 : 0) + (o.out_t ? sizeof(T) : 0));
+      } else if (o.kind == OP_INJ_C8) {
+        flops = 2.0 * rows * 8 * (8 + o.ctx);
+        bytes = rows * (8 * (sizeof(T) + 4) + o.ctx * sizeof(T) + 8 * ((o.out_r ? 4 : 0) + (o.out_t ? sizeof(T) : 0)));
+      } else if (o.kind == OP_D0_DOWN) {
+        flops = 2.0 * rows * 8;
+        bytes = rows * (4 + 32);
+      } else if (o.kind == OP_D0_UP) {
+        flops = 2.0 * rows * 8 * o.taps;
+        bytes = rows * (8 * sizeof(T) + 8);
+      }
+      snprintf(line, sizeof line, "%zu %s %d %d %d %.6f %.6e %.6e\n", i, kOpNames[o.kind], o.depth, o.stack, o.item, ms, flops, bytes);
+      out += line;
+    }
+    if ((int)out.size() + 1 > len) return fail(SFB_ERR_INVALID, "profile buffer too small: need %zu", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return SFB_OK;
+  }
 
   int ensure_plan(int64_t B, int64_t L, int cfg_on, int64_t rows, void* ws, size_t ws_bytes) {
     if (!finalized) return fail(SFB_ERR_STATE, "finalize first");
@@ -810,9 +858,15 @@ struct Engine : EngineBase {
     ++launches;
     int n = (int)plan.ops.size();
     if (op_limit >= 0 && op_limit < n) n = op_limit;
+    if (profiling && prof_ev.size() < 2 * plan.ops.size()) {
+      const size_t old = prof_ev.size();
+      prof_ev.resize(2 * plan.ops.size());
+      for (size_t k = old; k < prof_ev.size(); ++k) SFB_CUDA(cudaEventCreate(&prof_ev[k]));
+    }
     for (int i = 0; i < n; ++i) {
       const Op& o = plan.ops[i];
       const unsigned lb = (unsigned)((o.L + 255) / 256);
+      if (profiling) cudaEventRecord(prof_ev[2 * i], st);
       switch (o.kind) {
         case OP_D0_DOWN:
           d0_down_kernel<<<dim3(lb, o.B), 256, 0, st>>>(sc.x, o.w0, o.w1, o.out_r, o.stats_out, o.L, Bx);
@@ -869,6 +923,7 @@ struct Engine : EngineBase {
         }
       }
       ++launches;
+      if (profiling) cudaEventRecord(prof_ev[2 * i + 1], st);
     }
     SFB_CUDA(cudaGetLastError());
     return SFB_OK;
@@ -1096,6 +1151,15 @@ int sfb_dbg_set_op_limit(sfb_handle* h, int n_ops) {
 int sfb_dbg_plan_size(sfb_handle* h, int64_t B, int64_t L, int cfg_on, void* workspace, size_t workspace_bytes) {
   if (!h) return SFB_ERR_INVALID;
   return h->e->plan_size(B, L, cfg_on, workspace, workspace_bytes);
+}
+int sfb_dbg_profile(sfb_handle* h, int enable) {
+  if (!h) return SFB_ERR_INVALID;
+  h->e->profiling = enable != 0;
+  return SFB_OK;
+}
+int sfb_dbg_profile_report(sfb_handle* h, char* buf, int buf_len) {
+  if (!h || !buf) return SFB_ERR_INVALID;
+  return h->e->profile_report(buf, buf_len);
 }
 int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len) {
   if (!h || !buf) return SFB_ERR_INVALID;

@@ -219,6 +219,21 @@ class UNetV0:
                             nbytes=int(nbytes), rows=int(rows), cols=int(cols), dtype=int(dt)))
         return ops, ws
 
+    def profile(self, enable: bool):
+        """Bracket every launch of subsequent U-Net evaluations with CUDA events (see ``profile_report``)."""
+        self._check(self._lib.sfb_dbg_profile(self._h, int(enable)))
+
+    def profile_report(self):
+        """Per-op device time / algorithmic flops / bytes of the most recent profiled evaluation (sync first)."""
+        buf = C.create_string_buffer(1 << 17)
+        self._check(self._lib.sfb_dbg_profile_report(self._h, buf, len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            i, kind, depth, stack, item, ms, flops, nbytes = line.split()
+            rows.append(dict(index=int(i), kind=kind, depth=int(depth), stack=int(stack), item=int(item), ms=float(ms),
+                             flops=float(flops), bytes=float(nbytes)))
+        return rows
+
     def debug_set_op_limit(self, n: int):
         self._check(self._lib.sfb_dbg_set_op_limit(self._h, int(n)))
 

@@ -1,0 +1,233 @@
+"""Parity tests proper (need a B200): the CUDA path through the C ABI vs the oracle on the same seeded inputs.
+
+Tolerances (north_star): fp32 mode (TF32 MMA, fp32 storage): per-step relative L2 <= 1e-3; bf16 mode (bf16 operands,
+fp32 residual stream): per-step relative L2 <= 2e-2 on v (stated bound), far tighter on x_{i+1}.
+Integer / index work does not occur on this path."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.trace import trace_unet
+from tests.util import SMALL, make_inputs, make_oracle, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_V = {"fp32": 1e-3, "bf16": 2e-2}
+TOL_OP = {"fp32": 6e-3, "bf16": 5e-2}       # per-op intermediates (unattenuated by the skip / sampler scales)
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_device):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return cuda_device
+
+
+def _P(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p()
+
+
+def _build(dev, precision, cfg_kwargs=SMALL, upsample_mode="nearest", stress=True, seed=0):
+    import syncfusion_b200 as sf
+    om = make_oracle(cfg_kwargs, stress=stress, upsample_mode=upsample_mode, seed=seed)
+    m = sf.DiffusionModel(sf.UNetConfig(precision=precision, upsample_mode=upsample_mode, **cfg_kwargs), dev)
+    m.load_state_dict(om.net.state_dict())
+    return om.to(dev), m
+
+
+def _inputs(om, B, L, dev, seed=12345):
+    x, ch, e = make_inputs(om.net.cfg, B, L, seed=seed)
+    return x.to(dev), [c.to(dev) for c in ch], e.to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("bf16", [True, False])
+@pytest.mark.parametrize("case", [
+    # B, L, K1, K2, N, taps, bmod2, bias_mod, gs
+    (2, 256, 128, 0, 64, 3, 0, 0, 8), (2, 200, 32, 0, 32, 3, 0, 0, 4), (3, 64, 128, 0, 128, 3, 0, 0, 16),
+    (4, 256, 128, 32, 128, 1, 2, 0, 16), (2, 128, 64, 0, 128, 3, 0, 32, 4), (1, 384, 512, 0, 1536, 1, 0, 0, 0),
+    (2, 256, 1024, 0, 1024, 3, 0, 0, 128), (1, 1, 64, 0, 32, 3, 0, 0, 4),
+])
+def test_gemm_kernel(dev, bf16, case):
+    from syncfusion_b200 import _lib
+    lib = _lib.load()
+    B, L, K1, K2, N, taps, bmod2, bias_mod, gs = case
+    dt = torch.bfloat16 if bf16 else torch.float32
+    g = torch.Generator().manual_seed(1)
+    a1 = torch.randn(B, L, K1, generator=g).to(dev).to(dt)
+    a2 = torch.randn(max(bmod2, 1), L, max(K2, 8), generator=g).to(dev).to(dt) if K2 else None
+    w = (torch.randn(taps * N, K1 + K2, generator=g) / (taps * (K1 + K2)) ** 0.5).to(dev).to(dt)
+    bm = bias_mod or N
+    bias = torch.randn(bm, generator=g).to(dev)
+    resid = torch.randn(B, L, N, generator=g).to(dev)
+    out_r = torch.full((B, L, N), float("nan"), device=dev)
+    out_t = torch.zeros(B, L, N, device=dev, dtype=dt)
+    stats = torch.zeros(B, 8, 2, device=dev, dtype=torch.float64) if gs else None
+    rc = lib.sfb_dbg_gemm(int(bf16), _P(a1), _P(a2), _P(w), _P(bias), _P(resid), _P(out_r), _P(out_t), _P(stats), B, L,
+                          K1, K2, N, taps, max(bmod2, 1), bm, gs, C.c_void_p(0))
+    torch.cuda.synchronize()
+    assert rc == 0
+    A = F.pad(a1.float(), (0, 0, 1, 1)) if taps == 3 else a1.float()
+    ref = torch.zeros(B, L, N, device=dev)
+    for t in range(taps):
+        ref += (A[:, t:t + L] if taps == 3 else A) @ w.float()[t * N:(t + 1) * N, :K1].T
+    if K2:
+        ref += a2.float()[torch.arange(B, device=dev) % bmod2] @ w.float()[:N, K1:].T
+    ref += bias[torch.arange(N, device=dev) % bm] + resid
+    assert rel_l2(out_r, ref) < (1e-5 if bf16 else 2e-3)        # bf16 operands are exact inputs here; tf32 rounds
+    assert rel_l2(out_t.float(), ref) < 5e-3
+    if gs:
+        grp = (torch.arange(N, device=dev) % bm) // gs
+        s_ref = torch.zeros(B, 8, 2, device=dev, dtype=torch.float64)
+        for gi in range(8):
+            msk = grp == gi
+            if msk.any():
+                s_ref[:, gi, 0] = ref[:, :, msk].double().sum(dim=(1, 2))
+                s_ref[:, gi, 1] = (ref[:, :, msk].double() ** 2).sum(dim=(1, 2))
+        assert rel_l2(stats, s_ref) < 3e-3
+
+
+@pytest.mark.parametrize("bf16", [True, False])
+@pytest.mark.parametrize("B,N", [(1, 128), (2, 256), (2, 64), (1, 40), (1, 4), (2, 1024), (1, 4096)])
+def test_attention_kernel(dev, bf16, B, N):
+    from syncfusion_b200 import _lib
+    lib = _lib.load()
+    dt = torch.bfloat16 if bf16 else torch.float32
+    g = torch.Generator().manual_seed(N)
+    qkv = torch.randn(B, N, 1536, generator=g).to(dev).to(dt)
+    qkv[..., :512] *= 2.0
+    out = torch.zeros(B, N, 512, device=dev, dtype=dt)
+    assert lib.sfb_dbg_attention(int(bf16), _P(qkv), _P(out), B, N, C.c_void_p(0)) == 0
+    torch.cuda.synchronize()
+    q, k, v = (t.reshape(B, N, 8, 64).transpose(1, 2) for t in qkv.float().split(512, dim=-1))
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, 512)
+    assert rel_l2(out.float(), ref) < (1e-2 if bf16 else 4e-3)
+
+
+# ------------------------------------------------------------------------------------------------ U-Net evaluation
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("upsample_mode", ["nearest", "transpose"])
+@pytest.mark.parametrize("scale", [1.0, 2.0])
+def test_unet_layerwise_and_output(dev, precision, upsample_mode, scale):
+    """Every plan op vs the oracle trace (stress init), then v itself."""
+    om, m = _build(dev, precision, upsample_mode=upsample_mode)
+    B, L = 2, 1024
+    x, ch, e = _inputs(om, B, L, dev)
+    t = torch.tensor([0.7, 0.3], device=dev)
+    tr, v_ref = trace_unet(om.net, x, t, e, ch, scale)
+    net = m.net
+    v = net(x, t, embedding=e, embedding_scale=scale, channels=ch)
+    assert rel_l2(v, v_ref) < TOL_V[precision]
+    assert rel_l2(v - x, v_ref - x) < 10 * TOL_V[precision]
+    ops, ws = net.debug_ops(B, L, int(scale != 1.0))
+    assert len(ops) == len(tr)
+    tdt = torch.float32 if precision == "fp32" else torch.bfloat16
+    pad = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
+    try:
+        for i, (op, (kinds, ref)) in enumerate(zip(ops, tr)):
+            assert op["kind"] in kinds.split("|"), (i, op, kinds)
+            net.debug_set_op_limit(i + 1)
+            net(x, t, embedding=e, embedding_scale=scale, channels=ch)
+            torch.cuda.synchronize()
+            raw = ws[pad + op["off"]: pad + op["off"] + op["nbytes"]]
+            got = raw.view(torch.float32 if op["dtype"] == 0 else tdt).reshape(op["rows"], op["cols"]).float()
+            err = rel_l2(got, ref.reshape(op["rows"], op["cols"]))
+            assert err < TOL_OP[precision], (i, op["kind"], op["depth"], err)
+    finally:
+        net.debug_set_op_limit(-1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_full_architecture(dev, precision):
+    """The real exp/model/diffusion.yaml architecture (8 depths, 210 M parameters) at L = 8192, CFG on."""
+    om, m = _build(dev, precision, cfg_kwargs={})
+    x, ch, e = _inputs(om, 2, 8192, dev)
+    t = torch.tensor([0.9, 0.1], device=dev)
+    v_ref = om.net(x, t, embedding=e, embedding_scale=2.0, channels=ch)
+    v = m.net(x, t, embedding=e, embedding_scale=2.0, channels=ch)
+    assert rel_l2(v, v_ref) < TOL_V[precision]
+    assert rel_l2(v - x, v_ref - x) < 10 * TOL_V[precision]
+
+
+def test_cfg_scale_one_is_single_pass_and_affine(dev):
+    om, m = _build(dev, "fp32")
+    x, ch, e = _inputs(om, 2, 512, dev)
+    t = torch.full((2,), 0.5, device=dev)
+    v1, v2, v3 = (m.net(x, t, embedding=e, embedding_scale=s, channels=ch) for s in (1.0, 2.0, 3.0))
+    assert rel_l2(v3 - v2, v2 - v1) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("scale", [1.0, 2.0])
+def test_sample_teacher_forced_per_step(dev, precision, scale):
+    """SURVEY.md D.1 primary protocol: feed the oracle's x_i to both, compare v_i and x_{i+1} for every step."""
+    om, m = _build(dev, precision)
+    N, B, L = 6, 2, 2048
+    x, ch, e = _inputs(om, B, L, dev)
+    ref, xs, vs = om.sampler(x, N, channels=ch, embedding=e, embedding_scale=scale, return_trajectory=True)
+    teacher = torch.stack(xs[:-1])
+    out, tx, tv = m.net.sample(x, N, embedding=e, embedding_scale=scale, channels=ch, return_trajectory=True,
+                               teacher=teacher)
+    for i in range(N):
+        assert rel_l2(tv[i], vs[i]) < TOL_V[precision], ("v", i)
+        assert rel_l2(tx[i], xs[i + 1]) < TOL_V[precision] / 4, ("x", i)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sample_free_running_and_golden(dev, precision):
+    """Free-running 10-step CFG sample vs the oracle (secondary protocol), and the frozen golden fixture."""
+    import os
+    om, m = _build(dev, precision)
+    x, ch, e = _inputs(om, 2, 2048, dev)
+    ref = om.sample(x, num_steps=10, channels=ch, embedding=e, embedding_scale=2.0)
+    out = m.sample(x_noisy=x, num_steps=10, channels=ch, embedding=e, embedding_scale=2.0)
+    assert rel_l2(out, ref) < (1e-2 if precision == "fp32" else 5e-2)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "small_unet_golden.pt"))
+    xg, chg, eg = make_inputs(om.net.cfg, g["B"], g["L"])
+    outg = m.sample(x_noisy=xg.to(dev), num_steps=g["steps"], channels=[c.to(dev) for c in chg], embedding=eg.to(dev),
+                    embedding_scale=g["scale"])
+    assert rel_l2(outg.cpu(), g["sample"]) < (1e-2 if precision == "fp32" else 5e-2)
+
+
+def test_sampler_closed_form_properties(dev):
+    """Size-independent properties at the full L = 262144: sigma_N = 0 makes the last step return x_pred, the update
+    is linear in (x, v), and a zero-step-size identity holds."""
+    om, m = _build(dev, "fp32")
+    L = 262144
+    x, ch, e = _inputs(om, 1, L, dev)
+    out1, tx, tv = m.net.sample(x, 1, embedding=e, embedding_scale=1.0, channels=ch, return_trajectory=True)
+    # one step: sigma 1 -> 0: alpha=cos(pi/2)~0, beta=1: x_pred = -v (up to cos(pi/2) in fp32), x_1 = x_pred
+    a, b = torch.cos(torch.tensor(1.0) * torch.pi / 2).item(), 1.0
+    assert rel_l2(out1, a * x - b * tv[0]) < 1e-5
+    assert torch.equal(out1, tx[0])
+
+
+def test_argument_errors_mirror_upstream_asserts(dev):
+    om, m = _build(dev, "bf16")
+    x, ch, e = _inputs(om, 1, 512, dev)
+    with pytest.raises(AssertionError):
+        m.sample(x_noisy=x, num_steps=2, channels=ch, embedding=None, embedding_scale=1.0)
+    bad = list(ch); bad[1] = bad[1][:, :, :-1]
+    with pytest.raises(AssertionError):
+        m.sample(x_noisy=x, num_steps=2, channels=bad, embedding=e, embedding_scale=1.0)
+    with pytest.raises(AssertionError):
+        m.sample(x_noisy=x, num_steps=2, channels=ch[:2], embedding=e, embedding_scale=1.0)
+    with pytest.raises(AssertionError):
+        m.sample(x_noisy=x[:, :, :500], num_steps=2, channels=ch, embedding=e, embedding_scale=1.0)
+    with pytest.raises(AssertionError):
+        m.sample(x_noisy=x, num_steps=2, channels=ch, embedding=torch.cat([e, e], dim=1), embedding_scale=1.0)
+
+
+def test_batch_independence_and_determinism(dev):
+    """Clips are independent (what makes the multi-GPU sharding exact): a clip's result does not depend on its
+    batch-mates, and the run is bit-reproducible except for fp64-atomic GroupNorm statistics (<= 1e-6)."""
+    om, m = _build(dev, "bf16")
+    x, ch, e = _inputs(om, 3, 1024, dev)
+    full = m.sample(x_noisy=x, num_steps=3, channels=ch, embedding=e, embedding_scale=2.0)
+    one = m.sample(x_noisy=x[1:2], num_steps=3, channels=[c[1:2] for c in ch], embedding=e[1:2], embedding_scale=2.0)
+    assert rel_l2(one, full[1:2]) < 1e-5
+    again = m.sample(x_noisy=x, num_steps=3, channels=ch, embedding=e, embedding_scale=2.0)
+    assert rel_l2(again, full) < 1e-6

@@ -1,0 +1,13 @@
+#!/bin/bash
+# One GPU round: parity tests, bench, ncu launch list.  Usage: bash tools/gpu_round.sh [tests] [bench] [ncu]
+mkdir -p gpurun_out
+for what in "$@"; do
+case $what in
+tests) timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -n 15 gpurun_out/pytest_gpu.log;;
+bench) timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err;;
+benchcfg) timeout 900 python bench.py --steps 2 --warmup 3 --scale 2.0 --no-cpu-baseline > gpurun_out/bench_cfg.json 2> gpurun_out/bench_cfg.err; echo "bench exit $?"; cat gpurun_out/bench_cfg.json; tail -n 5 gpurun_out/bench_cfg.err;;
+ref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json;;
+ncu) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 125 -c 420 --csv --log-file gpurun_out/launches.csv python tools/ncu_step.py --steps 2 > gpurun_out/ncu_step.log 2>&1; tail -n 3 gpurun_out/ncu_step.log;;
+smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; tail -n 5 gpurun_out/smoke.log;;
+esac
+done
