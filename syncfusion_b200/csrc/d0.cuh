@@ -11,30 +11,40 @@
 
 namespace sfb {
 
-// per-channel (sum, sumsq) of 8 channels -> block reduce -> 16 f64 atomics
-__device__ __forceinline__ void stats8_block_reduce(const float* y, bool valid, double* stats_b, float* s_red /*[16]*/) {
-  float s[16];
+// per-channel (sum, sum of squares) of 8 channels over the block's 256 positions, accumulated in fp64: GroupNorm at
+// depth 0 is a per-channel instance norm, and E[x^2] - mean^2 cancels catastrophically in fp32 whenever a channel is
+// nearly constant (|mean| >> std).  Values go through smem; 64 threads each reduce 32 rows of one channel in double.
+struct Stats8Smem {
+  float y[256 * 9];
+  double red[16];
+};
+__device__ __forceinline__ void stats8_block_reduce(const float* y, bool valid, double* stats_b, Stats8Smem& sm) {
+  const int tid = threadIdx.x;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s[2 * j] = valid ? y[j] : 0.f; s[2 * j + 1] = valid ? y[j] * y[j] : 0.f; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) atomicAdd(&s_red[j], s[j]);
+  for (int j = 0; j < 8; ++j) sm.y[tid * 9 + j] = valid ? y[j] : 0.f;
+  if (tid < 16) sm.red[tid] = 0.0;
+  __syncthreads();
+  if (tid < 64) {
+    const int c = tid & 7, seg = tid >> 3;
+    double a = 0.0, q = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const double v = (double)sm.y[(i * 8 + seg) * 9 + c];
+      a += v;
+      q += v * v;
+    }
+    atomicAdd(&sm.red[c * 2], a);
+    atomicAdd(&sm.red[c * 2 + 1], q);
   }
   __syncthreads();
-  if (threadIdx.x < 16) atomicAdd(&stats_b[threadIdx.x], (double)s_red[threadIdx.x]);
+  if (tid < 16) atomicAdd(&stats_b[tid], sm.red[tid]);
 }
 
 // x [Bx, L] f32 (clip b % Bx) -> y [B, L, 8] f32 ; w [8], bias [8]
 __global__ void __launch_bounds__(256) d0_down_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y,
                                                       double* __restrict__ stats, int L, int Bx) {
-  __shared__ float s_red[16];
-  if (threadIdx.x < 16) s_red[threadIdx.x] = 0.f;
-  __syncthreads();
+  __shared__ Stats8Smem s_st;
   const int b = blockIdx.y;
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = l < L;
@@ -45,7 +55,7 @@ __global__ void __launch_bounds__(256) d0_down_kernel(const float* __restrict__ 
     for (int j = 0; j < 8; ++j) o[j] = xv * __ldg(&w[j]) + __ldg(&bias[j]);
     Vec8<float>::store(y + ((size_t)b * L + l) * 8, o);
   }
-  if (stats) stats8_block_reduce(o, valid, stats + (size_t)b * 16, s_red);
+  if (stats) stats8_block_reduce(o, valid, stats + (size_t)b * 16, s_st);
 }
 
 // in [B, L, 8] (T) ; w [24][8] f32 (k = tap * 8 + ci, co fastest) ; bias [8]
@@ -55,9 +65,8 @@ __global__ void __launch_bounds__(256) conv3_c8_kernel(const T* __restrict__ in,
                                                        const float* __restrict__ bias, const float* resid, float* out_r,
                                                        T* __restrict__ out_t, double* __restrict__ stats, int L) {
   __shared__ float s_w[24 * 8];
-  __shared__ float s_red[16];
+  __shared__ Stats8Smem s_st;
   if (threadIdx.x < 192) s_w[threadIdx.x] = w[threadIdx.x];
-  if (threadIdx.x < 16) s_red[threadIdx.x] = 0.f;
   __syncthreads();
   const int b = blockIdx.y;
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(256) conv3_c8_kernel(const T* __restrict__ in,
     if (out_r) Vec8<float>::store(out_r + g, acc);
     if (out_t) store_operand8<T>(out_t + g, acc);
   }
-  if (stats) stats8_block_reduce(acc, valid, stats + (size_t)b * 16, s_red);
+  if (stats) stats8_block_reduce(acc, valid, stats + (size_t)b * 16, s_st);
 }
 
 // m_t [B, L, 8] (T operand copy), m_r [B, L, 8] f32 (residual), ctx [Bc, L, CTX] (T), w [8 + CTX][8] f32 (k, co), bias [8],
@@ -102,9 +111,8 @@ __global__ void __launch_bounds__(256) inject_c8_kernel(const T* __restrict__ m_
                                                         const float* __restrict__ xbias, float* out_r, T* __restrict__ out_t,
                                                         double* __restrict__ stats, int L, int Bc, int xb_stride) {
   __shared__ float s_w[(8 + CTX) * 8];
-  __shared__ float s_red[16];
+  __shared__ Stats8Smem s_st;
   for (int i = threadIdx.x; i < (8 + CTX) * 8; i += blockDim.x) s_w[i] = w[i];
-  if (threadIdx.x < 16) s_red[threadIdx.x] = 0.f;
   __syncthreads();
   const int b = blockIdx.y;
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(256) inject_c8_kernel(const T* __restrict__ m_
     if (out_r) Vec8<float>::store(out_r + g, acc);
     if (out_t) store_operand8<T>(out_t + g, acc);
   }
-  if (stats) stats8_block_reduce(acc, valid, stats + (size_t)b * 16, s_red);
+  if (stats) stats8_block_reduce(acc, valid, stats + (size_t)b * 16, s_st);
 }
 
 // c [B, L, 8] (T) ; w [taps][8] f32 ; v[b, l] = x[b % Bx, l] + s[b % smod] * (sum w c + bias)

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   constexpr int kStage = gemm_stage_bytes<T, BN>();
   constexpr int kABytes = kGemmBM * 128;
   constexpr int kBBytes = BN * 128;
-  static_assert(kGemmBM * (BN + 1) * 4 <= kGemmStages * kStage, "staging tile must fit in the pipeline buffers");
+  static_assert(kGemmBM * (BN + 4) * 4 <= kGemmStages * kStage, "staging tile must fit in the pipeline buffers");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
   uint64_t* empty_bar = full_bar + kGemmStages;
   uint64_t* tmem_full_bar = empty_bar + kGemmStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* sacc = reinterpret_cast<float*>(tmem_slot + 2);   // [8][2] group partials
+  double* sacc = reinterpret_cast<double*>(tmem_slot + 2);   // [8][2] group partials (fp64: no cancellation in var)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (threadIdx.x < 16) sacc[threadIdx.x] = 0.f;
+  if (threadIdx.x < 16) sacc[threadIdx.x] = 0.0;
   if (warp == 1) { tmem_alloc(tmem_slot, BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
@@ -137,10 +137,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
     const int e = threadIdx.x - 64;          // 0..127
     float* stile = reinterpret_cast<float*>(smem);
-    constexpr int LD = BN + 1;
+    constexpr int LD = BN + 4;               // row pitch: 16-byte aligned rows, conflict-free 128-bit accesses
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    {
+    {   // phase 1: TMEM -> registers -> staging tile (thread = accumulator row)
       const int r = q * 32 + lane;
       const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
 #pragma unroll 1
@@ -149,46 +149,98 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const __grid_c
         tmem_ld32(trow + c, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(v[j]);
-          if (p.bias) a += __ldg(&p.bias[(n0 + c + j) % p.bias_mod]);
-          stile[r * LD + c + j] = a;
-        }
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(&stile[r * LD + c + j]) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
     tc_fence_before();
     asm volatile("bar.sync 1, 128;" ::: "memory");
+    // phase 2: coalesced row-major pass, 4 columns per lane (x2 for BN = 256), U rows in flight per thread
     const int rows_valid = min(kGemmBM, p.rows_per_clip - l0);
-    constexpr int CP = BN < 128 ? BN : 128;  // columns handled per pass
-    constexpr int RG = 128 / CP;             // row groups
-    const int rg = e / CP;
+    constexpr int LPR = BN >= 128 ? 32 : BN / 4;   // lanes per row
+    constexpr int RPI = 32 / LPR;                  // rows per warp iteration
+    constexpr int NCH = BN >= 256 ? 2 : 1;         // float4 chunks per lane per row
+    constexpr int ITERS = 32 / RPI;                // iterations per warp (4 warps x RPI rows x ITERS = 128 rows)
+    constexpr int U = 4;
+    const int ew = warp - 2;
+    const int sub = lane % LPR, rsub = lane / LPR;
+    float4 bias4[NCH], cs4[NCH], rv4[NCH];
+    int nm0[NCH];
+#pragma unroll
+    for (int jj = 0; jj < NCH; ++jj) {
+      const int col = jj * 128 + sub * 4;
+      nm0[jj] = (n0 + col) % p.bias_mod;           // 4 | bias_mod and 4 | (n0 + col): the 4 columns never wrap
+      bias4[jj] = p.bias ? *reinterpret_cast<const float4*>(p.bias + nm0[jj]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      cs4[jj] = p.colscale ? *reinterpret_cast<const float4*>(p.colscale + (size_t)(b % (p.cs_bmod > 0 ? p.cs_bmod : 1)) * p.cs_bstride + nm0[jj])
+                           : make_float4(1.f, 1.f, 1.f, 1.f);
+      rv4[jj] = p.rowvec ? *reinterpret_cast<const float4*>(p.rowvec + (size_t)b * p.rowvec_stride + nm0[jj])
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double s1[NCH][4], s2[NCH][4];   // fp64 accumulation (only when stats are requested)
+#pragma unroll
+    for (int jj = 0; jj < NCH; ++jj)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s1[jj][i] = 0.0; s2[jj][i] = 0.0; }
+    const size_t gbase = ((size_t)b * p.rows_per_clip + l0) * p.N + n0 + sub * 4;
 #pragma unroll 1
-    for (int cb = 0; cb < BN; cb += CP) {
-      const int col = cb + (e % CP);
-      const int n = n0 + col;
-      const int nm = n % p.bias_mod;
-      const float cs = p.colscale ? __ldg(&p.colscale[(size_t)(b % (p.cs_bmod > 0 ? p.cs_bmod : 1)) * p.cs_bstride + nm]) : 1.f;
-      const float rv = p.rowvec ? __ldg(&p.rowvec[(size_t)b * p.rowvec_stride + nm]) : 0.f;
-      float s1 = 0.f, s2 = 0.f;
-      size_t g = ((size_t)b * p.rows_per_clip + l0 + rg) * p.N + n;
-      const size_t gstep = (size_t)RG * p.N;
-      for (int r = rg; r < rows_valid; r += RG, g += gstep) {
-        float v = stile[r * LD + col] * cs + rv;
-        if (p.resid) v += __ldg(&p.resid[g]);
-        if (p.out_r) p.out_r[g] = v;
-        if (p.out_t) p.out_t[g] = from_f32<T>(v);
-        s1 += v;
-        s2 += v * v;
+    for (int it0 = 0; it0 < ITERS; it0 += U) {
+      float4 res[U][NCH];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = (it0 + u) * (4 * RPI) + ew * RPI + rsub;
+#pragma unroll
+        for (int jj = 0; jj < NCH; ++jj)
+          res[u][jj] = (p.resid && r < rows_valid) ? *reinterpret_cast<const float4*>(p.resid + gbase + (size_t)r * p.N + jj * 128)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (p.stats) {
-        const int grp = nm / p.gs;
-        atomicAdd(&sacc[grp * 2 + 0], s1);
-        atomicAdd(&sacc[grp * 2 + 1], s2);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = (it0 + u) * (4 * RPI) + ew * RPI + rsub;
+        if (r < rows_valid) {
+#pragma unroll
+          for (int jj = 0; jj < NCH; ++jj) {
+            const float4 a = *reinterpret_cast<const float4*>(&stile[r * LD + jj * 128 + sub * 4]);
+            float v[4];
+            v[0] = (a.x + bias4[jj].x) * cs4[jj].x + rv4[jj].x + res[u][jj].x;
+            v[1] = (a.y + bias4[jj].y) * cs4[jj].y + rv4[jj].y + res[u][jj].y;
+            v[2] = (a.z + bias4[jj].z) * cs4[jj].z + rv4[jj].z + res[u][jj].z;
+            v[3] = (a.w + bias4[jj].w) * cs4[jj].w + rv4[jj].w + res[u][jj].w;
+            const size_t g = gbase + (size_t)r * p.N + jj * 128;
+            if (p.out_r) *reinterpret_cast<float4*>(p.out_r + g) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.out_t) {
+              if constexpr (sizeof(T) == 2) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+                *reinterpret_cast<uint2*>(p.out_t + g) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+              } else {
+                *reinterpret_cast<float4*>(p.out_t + g) = make_float4(from_f32<float>(v[0]), from_f32<float>(v[1]), from_f32<float>(v[2]), from_f32<float>(v[3]));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (p.stats) { const double dv = (double)v[i]; s1[jj][i] += dv; s2[jj][i] += dv * dv; }
+            }
+          }
+        }
       }
     }
     if (p.stats) {
+#pragma unroll
+      for (int jj = 0; jj < NCH; ++jj) {
+        if (p.gs >= 4) {     // the lane's 4 columns share a group
+          const int grp = nm0[jj] / p.gs;
+          atomicAdd(&sacc[grp * 2 + 0], s1[jj][0] + s1[jj][1] + s1[jj][2] + s1[jj][3]);
+          atomicAdd(&sacc[grp * 2 + 1], s2[jj][0] + s2[jj][1] + s2[jj][2] + s2[jj][3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int grp = (nm0[jj] + i) / p.gs;
+            atomicAdd(&sacc[grp * 2 + 0], s1[jj][i]);
+            atomicAdd(&sacc[grp * 2 + 1], s2[jj][i]);
+          }
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (e < 16 && sacc[e] != 0.f) atomicAdd(&p.stats[(size_t)b * 16 + e], (double)sacc[e]);
+      if (e < 16 && sacc[e] != 0.0) atomicAdd(&p.stats[(size_t)b * 16 + e], sacc[e]);
     }
   }
   __syncthreads();

@@ -412,6 +412,11 @@ struct Engine : EngineBase {
         ftw.insert(ftw.end(), w->v.begin(), w->v.end());
         ftb.insert(ftb.end(), b->v.begin(), b->v.end());
         F_total += Cin;
+        while (F_total % 4) {   // keep every table segment 16-byte aligned (vector loads in the GEMM epilogue)
+          ftw.insert(ftw.end(), MF, 0.f);
+          ftb.push_back(0.f);
+          ++F_total;
+        }
       }
       // ---- items
       for (int s = 0; s < 2; ++s) {
