@@ -27,6 +27,12 @@ template <typename T> struct AttnCfg;
 template <> struct AttnCfg<__nv_bfloat16> { static constexpr int BKV = 128; };
 template <> struct AttnCfg<float> { static constexpr int BKV = 64; };
 
+__device__ __forceinline__ float fast_exp2(float x) {   // single MUFU.EX2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int kAttnThreads = 192;
 constexpr int kHeadDim = 64;
 
@@ -34,11 +40,11 @@ template <typename T>
 __host__ __device__ constexpr int attn_smem_bytes() {
   constexpr int DA = kHeadDim / ElemTraits<T>::kAtomElems;
   constexpr int BKV = AttnCfg<T>::BKV;
-  return DA * 128 * 128 /*Q*/ + 2 * 2 * DA * BKV * 128 /*K,V x 2 stages*/ + 2 * 128 * 128 /*P*/ + 1024 + 256;
+  return DA * 128 * 128 /*Q*/ + 2 * 2 * DA * BKV * 128 /*K,V x 2 stages*/ + 2 * 128 * 128 /*P*/ + 256;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_constant__ AttnParams<T> p) {
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_constant__ AttnParams<T> p) {
   using TR = ElemTraits<T>;
   constexpr int AE = TR::kAtomElems;            // elements per 128-byte row
   constexpr int DA = kHeadDim / AE;             // atoms along head dim (1 bf16, 2 tf32)
@@ -50,8 +56,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
   constexpr int kPBytes = PA * 128 * 128;
   constexpr uint32_t kTmemCols = 256;           // S: [0, BKV), O_j: [BKV, BKV + 64)
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + kQBytes;                  // stage s: K at sKV + s*2*kKBytes, V right after K
   uint8_t* sP = sKV + 4 * kKBytes;
@@ -166,29 +171,41 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       float mx = m_run;
+      const bool full_tile = kv_valid == BKV;   // tile-uniform: only the last tile of a ragged sequence is masked
 #pragma unroll 1
       for (int c = 0; c < BKV; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_off + c, v);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
       const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - mx) * sc);
       const float moff = mx * sc;
-      float rs = 0.f;
+      float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BKV; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_off + c, v);
         tmem_ld_wait();
         float pv[32];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = (c + i < kv_valid) ? exp2f(__uint_as_float(v[i]) * sc - moff) : 0.f;
-          pv[i] = e;
+          for (int i = 0; i < 32; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(v[i]), sc, -moff));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pv[i] = (c + i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), sc, -moff)) : 0.f;
         }
+        // row sum in fp32 on the un-rounded probabilities (two independent chains); the operand-precision rounding of
+        // P is zero-mean, so the normaliser differs from sum(round(P)) by ~1e-4 relative at most.
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) { rs0 += pv[i]; rs1 += pv[i + 1]; }
         // write this row's 32 probabilities into the swizzled K-major P tile (operand precision)
         if constexpr (sizeof(T) == 2) {
           const int atom = c / AE;               // 64 keys per atom
@@ -200,7 +217,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
             for (int t = 0; t < 4; ++t) {
               __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[ch * 8 + 2 * t], pv[ch * 8 + 2 * t + 1]);
               w[t] = *reinterpret_cast<uint32_t*>(&h2);
-              rs += __bfloat162float(h2.x) + __bfloat162float(h2.y);
             }
             uint4* dst = reinterpret_cast<uint4*>(sP + atom * 128 * 128 + r * 128 + ((cc ^ (r & 7)) * 16));
             *dst = make_uint4(w[0], w[1], w[2], w[3]);
@@ -210,12 +226,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_tc_kernel(const __grid_c
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {       // 8 chunks of 4 keys
             uint4* dst = reinterpret_cast<uint4*>(sP + atom * 128 * 128 + r * 128 + ((ch ^ (r & 7)) * 16));
-            *dst = make_uint4(__float_as_uint(pv[ch * 4]), __float_as_uint(pv[ch * 4 + 1]),
-                              __float_as_uint(pv[ch * 4 + 2]), __float_as_uint(pv[ch * 4 + 3]));
-            rs += pv[ch * 4] + pv[ch * 4 + 1] + pv[ch * 4 + 2] + pv[ch * 4 + 3];
+            *dst = make_uint4(__float_as_uint(from_f32<float>(pv[ch * 4])), __float_as_uint(from_f32<float>(pv[ch * 4 + 1])),
+                              __float_as_uint(from_f32<float>(pv[ch * 4 + 2])), __float_as_uint(from_f32<float>(pv[ch * 4 + 3])));
           }
         }
       }
+      const float rs = rs0 + rs1;
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(p_ready);

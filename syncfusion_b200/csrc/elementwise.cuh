@@ -64,30 +64,47 @@ __global__ void __launch_bounds__(256) gn_apply_silu_kernel(const Tin* __restric
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             Tout* __restrict__ out, int L, int C, int gs, float eps) {
   extern __shared__ float s_ab[];
+  __shared__ float s_g[16];   // per group: mean, rstd
   const int b = blockIdx.y;
-  const double cnt = (double)L * gs;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / gs;
-    const double s1 = stats[(size_t)b * 16 + g * 2], s2 = stats[(size_t)b * 16 + g * 2 + 1];
+  if (threadIdx.x < 8) {
+    const double cnt = (double)L * gs;
+    const double s1 = stats[(size_t)b * 16 + threadIdx.x * 2], s2 = stats[(size_t)b * 16 + threadIdx.x * 2 + 1];
     const double mean = s1 / cnt;
     double var = s2 / cnt - mean * mean;
     var = var > 0 ? var : 0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float a = rstd * gamma[c];
-    s_ab[c] = a;
-    s_ab[C + c] = beta[c] - (float)mean * a;
+    s_g[threadIdx.x * 2] = (float)mean;
+    s_g[threadIdx.x * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / gs;
+    const float a = s_g[g * 2 + 1] * gamma[c];
+    s_ab[c] = a;
+    s_ab[C + c] = beta[c] - s_g[g * 2] * a;
+  }
+  __syncthreads();
+  constexpr int U = 4;   // independent 128-bit loads in flight per thread
   const size_t nvec = (size_t)L * C / 8;
   const Tin* src = in + (size_t)b * L * C;
   Tout* dst = out + (size_t)b * L * C;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-    const int c0 = (int)((i * 8) % C);
-    float v[8];
-    Vec8<Tin>::load(src + i * 8, v);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * U) {
+    float v[U][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j] * s_ab[c0 + j] + s_ab[C + c0 + j]);
-    store_operand8<Tout>(dst + i * 8, v);
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < nvec) Vec8<Tin>::load(src + i * 8, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < nvec) {
+        const int c0 = (int)((i * 8) % C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = silu_f(v[u][j] * s_ab[c0 + j] + s_ab[C + c0 + j]);
+        store_operand8<Tout>(dst + i * 8, v[u]);
+      }
+    }
   }
 }
 

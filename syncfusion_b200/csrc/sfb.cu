@@ -152,9 +152,20 @@ struct EngineBase {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
 template <typename T, int BN>
-void launch_gemm_bn(const GemmParams<T>& p, int B, cudaStream_t st) {
-  dim3 grid(B * p.tiles_per_clip, p.N / BN);
+void launch_gemm_bn(GemmParams<T> p, int B, cudaStream_t st) {
+  p.n_tiles = p.N / BN;
+  p.total_tiles = B * p.tiles_per_clip * p.n_tiles;
+  const int grid = std::min(p.total_tiles, num_sms() * GemmCfg<BN>::kCtasPerSm);   // persistent CTAs
   gemm_tc_kernel<T, BN><<<grid, kGemmThreads, gemm_smem_bytes<T, BN>(), st>>>(p);
 }
 template <typename T>
@@ -181,7 +192,7 @@ cudaError_t set_kernel_attrs() {
   return e;
 }
 int pick_bn(int N) {
-  if (N % 256 == 0) return 256;
+  if (N % 256 == 0 && N >= 1024) return 256;
   if (N % 128 == 0) return 128;
   if (N == 64) return 64;
   if (N == 32) return 32;
@@ -878,7 +889,7 @@ struct Engine : EngineBase {
           break;
         case OP_GN: {
           const size_t nvec = (size_t)o.L * o.C / 8;
-          unsigned bpc = (unsigned)std::min<size_t>(std::max<size_t>((nvec + 2047) / 2048, 1), 2048);
+          unsigned bpc = (unsigned)std::min<size_t>(std::max<size_t>((nvec + 1023) / 1024, 1), 8192);
           const size_t sm = (size_t)2 * o.C * sizeof(float);
           if (o.in_is_f32)
             gn_apply_silu_kernel<float, T><<<dim3(bpc, o.B), 256, sm, st>>>(reinterpret_cast<const float*>(o.in), o.stats_in, o.w0, o.w1,

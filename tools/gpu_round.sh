@@ -8,6 +8,9 @@ bench) timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/bench.json 
 benchcfg) timeout 900 python bench.py --steps 2 --warmup 3 --scale 2.0 --no-cpu-baseline > gpurun_out/bench_cfg.json 2> gpurun_out/bench_cfg.err; echo "bench exit $?"; cat gpurun_out/bench_cfg.json; tail -n 5 gpurun_out/bench_cfg.err;;
 ref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json;;
 ncu) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 125 -c 420 --csv --log-file gpurun_out/launches.csv python tools/ncu_step.py --steps 2 > gpurun_out/ncu_step.log 2>&1; tail -n 3 gpurun_out/ncu_step.log;;
+ncufull32) timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'gemm_tc_kernel<__nv_bfloat16, .int.32>' -s 1 -c 2 -f -o gpurun_out/prof_gemm32 python tools/ncu_step.py --steps 1 > gpurun_out/ncu_full32.log 2>&1; tail -n 2 gpurun_out/ncu_full32.log;;
+ncufull256) timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'gemm_tc_kernel<__nv_bfloat16, .int.256>' -s 20 -c 2 -f -o gpurun_out/prof_gemm256 python tools/ncu_step.py --steps 1 > gpurun_out/ncu_full256.log 2>&1; tail -n 2 gpurun_out/ncu_full256.log;;
+ncuattn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -s 0 -c 1 -f -o gpurun_out/prof_attn python tools/ncu_step.py --steps 1 > gpurun_out/ncu_attn.log 2>&1; tail -n 2 gpurun_out/ncu_attn.log;;
 smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; tail -n 5 gpurun_out/smoke.log;;
 esac
 done
