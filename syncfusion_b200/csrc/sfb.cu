@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -19,6 +20,7 @@
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
 #include "prepare.cuh"
+#include "rk_tc.cuh"
 
 using namespace sfb;
 
@@ -87,6 +89,19 @@ template <> __nv_bfloat16 host_cvt<__nv_bfloat16>(float v) { return __float2bflo
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Row-major [taps * N][Kw] fp32 -> bf16 tiles [taps][ceil(Kw / 64)][N][64] (K zero padded): one resident UMMA B tile
+// (128-byte rows, loaded with a 128B-swizzle TMA box [64, N]) per (tap, 64-wide K atom).  Appends to `out`.
+void pack_tiles(std::vector<__nv_bfloat16>& out, const float* Wm, int taps, int N, int Kw) {
+  const int KA = (Kw + 63) / 64;
+  for (int t = 0; t < taps; ++t)
+    for (int a = 0; a < KA; ++a)
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < 64; ++k) {
+          const int kk = a * 64 + k;
+          out.push_back(__float2bfloat16_rn(kk < Kw ? Wm[((size_t)t * N + n) * Kw + kk] : 0.f));
+        }
+}
+
 struct GemmW {           // re-packed weights of one contraction
   void* w = nullptr;     // [taps * N][Kw] operand precision
   float* bias = nullptr; // [bias_mod] or null
@@ -94,6 +109,8 @@ struct GemmW {           // re-packed weights of one contraction
 };
 
 struct ItemW {
+  void *rk1_w = nullptr, *rk2_w = nullptr;   // tile-packed resident weights (rk_tc.cuh): conv1 | conv2 + inject
+  int rk1_id = -1, rk2_id = -1;
   float *gn1_g = nullptr, *gn1_b = nullptr, *gn2_g = nullptr, *gn2_b = nullptr;
   GemmW conv1, conv2, inject, qkv, out;
   float *c8_w1 = nullptr, *c8_b1 = nullptr, *c8_w2 = nullptr, *c8_b2 = nullptr, *c8_wi = nullptr, *c8_bi = nullptr;
@@ -103,6 +120,8 @@ struct ItemW {
 };
 struct DepthW {
   GemmW down, up;
+  void *rk_down_w = nullptr, *rk_up_w = nullptr;
+  int rk_down_id = -1, rk_up_id = -1;
   float *c8_dw = nullptr, *c8_db = nullptr, *c8_uw = nullptr;
   float c8_ub = 0.f;
   int up_taps = 1;
@@ -110,8 +129,8 @@ struct DepthW {
   int skip_off = 0;
 };
 
-enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN };
-const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn"};
+enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN, OP_RK };
+const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn", "rk"};
 
 struct EngineBase {
   sfb_unet_config cfg;
@@ -230,6 +249,7 @@ struct Engine : EngineBase {
   float *t_w = nullptr, *t_lw = nullptr, *t_lb = nullptr, *t_mw = nullptr, *t_mb = nullptr, *fixed_emb = nullptr;
   float *ft_w = nullptr, *ft_b = nullptr;   // concatenated Linear(SiLU(features)) weights [F_total][MF]
   int F_total = 0, XB_total = 0, n_gn = 0;
+  bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aid: force the unfused generic path everywhere
 
   struct Op {
     int kind = 0, depth = 0, stack = 0, item = 0;
@@ -246,6 +266,10 @@ struct Engine : EngineBase {
     int ft_off = -1;      // feature-table column offset (Modulation scale | SkipModulate scale), -1: none
     GemmParams<T> gp;
     AttnParams<T> ap;
+    RkParams rp;
+    int rk_id = -1;
+    double flops = 0, bytes = 0;   // algorithmic work of an OP_RK op (set at build time)
+    const char* ck = "";           // oracle-trace checkpoint this op's output equals (tests/trace.py)
     int BN = 0;
     size_t dbg_off = 0, dbg_bytes = 0;
     int dbg_rows = 0, dbg_cols = 0, dbg_dtype = 0;
@@ -302,7 +326,7 @@ struct Engine : EngineBase {
   }
 
   // conv weight [Co][Ci][taps] -> [taps*Co][Ci]
-  bool pack_conv3(const std::string& base, int C, GemmW& g) {
+  bool pack_conv3(const std::string& base, int C, GemmW& g, std::vector<float>* keep = nullptr) {
     const HostTensor* w = get(base + ".weight", {C, C, 3});
     const HostTensor* b = get(base + ".bias", {C});
     if (!w || !b) return false;
@@ -313,8 +337,10 @@ struct Engine : EngineBase {
     g.w = upload_T(r);
     g.bias = upload_f(b);
     g.N = C; g.K1 = C; g.K2 = 0; g.taps = 3; g.bias_mod = C;
+    if (keep) keep->swap(r);
     return g.w && g.bias;
   }
+  static constexpr bool kBF16 = sizeof(T) == 2;   // the resident-weight fused kernels (rk_tc.cuh) exist for bf16 operands
 
   int finalize() override {
     const sfb_unet_config& c = cfg;
@@ -334,6 +360,7 @@ struct Engine : EngineBase {
     }
     if (c.attentions[0]) return fail(SFB_ERR_UNSUPPORTED, "self-attention at depth 0 unsupported");
     if (set_kernel_attrs<T>() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (kBF16 && rk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (rk) failed: %s", cudaGetErrorString(cudaGetLastError()));
 
     // time conditioning (A.3)
     t_w = upload_f(get("time.weights", {128}));
@@ -367,6 +394,11 @@ struct Engine : EngineBase {
               for (int j = 0; j < f; ++j) r[(size_t)co * f * Cin + j * Cin + ci] = w->v[((size_t)co * Cin + ci) * f + j];
           W.down.w = upload_T(r); W.down.bias = upload_f(b);
           W.down.N = C; W.down.K1 = f * Cin; W.down.taps = 1; W.down.bias_mod = C;
+          if (kBF16 && !no_rk && (W.rk_down_id = rk_find(f * Cin, C, 1, 0, 0, C, 1)) >= 0) {
+            std::vector<__nv_bfloat16> tiles;
+            pack_tiles(tiles, r.data(), 1, C, f * Cin);
+            W.rk_down_w = upload<__nv_bfloat16>(tiles);
+          }
         }
       }
       // ---- Up (A.6, both modes)
@@ -386,6 +418,11 @@ struct Engine : EngineBase {
               for (int j = 0; j < f; ++j) r[((size_t)j * Cin + co) * C + ci] = w->v[((size_t)ci * Cin + co) * f + j];
           W.up.w = upload_T(r); W.up.bias = upload_f(b);
           W.up.N = f * Cin; W.up.K1 = C; W.up.taps = 1; W.up.bias_mod = Cin;
+          if (kBF16 && !no_rk && (W.rk_up_id = rk_find(C, f * Cin, 1, 0, 0, Cin, 1)) >= 0) {
+            std::vector<__nv_bfloat16> tiles;
+            pack_tiles(tiles, r.data(), 1, f * Cin, C);
+            W.rk_up_w = upload<__nv_bfloat16>(tiles);
+          }
         }
       } else {
         const HostTensor* w = get(P + "up.conv.weight", {Cin, C, 3});
@@ -412,6 +449,11 @@ struct Engine : EngineBase {
             }
           W.up.w = upload_T(r); W.up.bias = upload_f(b);
           W.up.N = N; W.up.K1 = C; W.up.taps = 3; W.up.bias_mod = Cin;
+          if (kBF16 && !no_rk && (W.rk_up_id = rk_find(C, N, 3, 0, 0, Cin, 1)) >= 0) {
+            std::vector<__nv_bfloat16> tiles;
+            pack_tiles(tiles, r.data(), 3, N, C);
+            W.rk_up_w = upload<__nv_bfloat16>(tiles);
+          }
         }
       }
       // ---- SkipModulate Linear (A.5)
@@ -434,6 +476,7 @@ struct Engine : EngineBase {
         W.items[s].assign(c.items[d], ItemW());
         for (int i = 0; i < c.items[d]; ++i) {
           ItemW& I = W.items[s][i];
+          std::vector<float> keep1, keep2;   // host copies of the conv weights [3 * C][C] for the resident tile packs
           char ip[96];
           snprintf(ip, sizeof ip, "d%d.items_%s.%d.", d, s == 0 ? "down" : "up", i);
           const std::string Q(ip);
@@ -455,7 +498,7 @@ struct Engine : EngineBase {
               (k ? I.c8_b2 : I.c8_b1) = upload_f(b);
             }
           } else {
-            if (!pack_conv3(Q + "resnet.conv1", C, I.conv1) || !pack_conv3(Q + "resnet.conv2", C, I.conv2))
+            if (!pack_conv3(Q + "resnet.conv1", C, I.conv1, &keep1) || !pack_conv3(Q + "resnet.conv2", C, I.conv2, &keep2))
               return err.empty() ? fail(SFB_ERR_CUDA, "weight upload failed") : SFB_ERR_MISSING;
           }
           {  // Modulation Linear(MF -> 2C)
@@ -480,6 +523,17 @@ struct Engine : EngineBase {
             } else {
               I.inject.w = upload_T(w->v); I.inject.bias = upload_f(b);
               I.inject.N = C; I.inject.K1 = C; I.inject.K2 = ctx; I.inject.taps = 1; I.inject.bias_mod = C;
+              // fused item: R1 = GN1+SiLU -> conv1 ; R2 = GN2+SiLU -> conv2 + x -> Modulation -> inject  (rk_tc.cuh)
+              const int id1 = rk_find(C, C, 3, 2, 0, C, 0), id2 = rk_find(C, C, 3, 1, 2, C, 1);
+              if (kBF16 && !no_rk && id1 >= 0 && id2 >= 0 && ctx % 8 == 0 && ctx <= rk_ctx_capacity(C)) {
+                std::vector<__nv_bfloat16> t1, t2;
+                pack_tiles(t1, keep1.data(), 3, C, C);
+                pack_tiles(t2, keep2.data(), 3, C, C);
+                pack_tiles(t2, w->v.data(), 1, C, C + ctx);
+                I.rk1_w = upload<__nv_bfloat16>(t1);
+                I.rk2_w = upload<__nv_bfloat16>(t2);
+                I.rk1_id = id1; I.rk2_id = id2;
+              }
             }
           } else {
             return fail(SFB_ERR_UNSUPPORTED, "context_channels[%d] == 0 unsupported", d);
@@ -621,6 +675,34 @@ struct Engine : EngineBase {
     p.stats = op.stats_out;
     return true;
   }
+  // Resident-weight fused op (rk_tc.cuh): A / W maps and tile bookkeeping; the caller adds R / T / C maps and vectors.
+  bool add_rk(Op& op, int id, const void* a, const void* wt, int L, int Beff) {
+    const RkKey k = rk_key(id);
+    op.kind = OP_RK; op.rk_id = id; op.B = Beff; op.L = L; op.C = k.N;
+    RkParams& p = op.rp;
+    memset(&p, 0, sizeof p);
+    const int rows_a = k.TAPS == 3 ? 136 : 128;
+    const int KA = (k.K1 + 63) / 64, KA2 = k.EPI == 2 ? (k.N + 64) / 64 : 0;
+    if (k.XF == 2) { if (!make_tmap3<float>(&p.tmA, a, k.K1, L, Beff, 32, rows_a)) return false; }
+    else if (!make_tmap3<__nv_bfloat16>(&p.tmA, a, k.K1, L, Beff, 64, rows_a)) return false;
+    if (!make_tmap2<__nv_bfloat16>(&p.tmW, wt, 64, (uint64_t)(k.TAPS * KA + KA2) * k.N, 64, k.N)) return false;
+    p.tmR = p.tmA; p.tmT = p.tmA; p.tmC = p.tmA;
+    p.L = L; p.tiles_per_clip = (L + 127) / 128; p.total_tiles = Beff * p.tiles_per_clip;
+    p.cs_bmod = 1; p.mod_bmod = 1; p.ctx_bmod = 1;
+    p.eps = 1e-5f;
+    return true;
+  }
+  bool rk_out_r(Op& op, float* ptr, bool resid) {
+    const RkKey k = rk_key(op.rk_id);
+    op.out_r = ptr; op.rp.has_out_r = 1; op.rp.has_resid = resid ? 1 : 0;
+    if (resid) op.resid = ptr;
+    return make_tmap3<float>(&op.rp.tmR, ptr, k.N, op.L, op.B, 32, 128);
+  }
+  bool rk_out_t(Op& op, void* ptr) {
+    const RkKey k = rk_key(op.rk_id);
+    op.out_t = ptr; op.rp.has_out_t = 1;
+    return make_tmap3<__nv_bfloat16>(&op.rp.tmT, ptr, k.N, op.L, op.B, 64, 128);
+  }
   void set_dbg(Op& op, int rows, int cols) {
     if (op.out_r) { op.dbg_off = (uint8_t*)op.out_r - wsb; op.dbg_dtype = 0; op.dbg_bytes = (size_t)rows * cols * 4; }
     else { op.dbg_off = (uint8_t*)op.out_t - wsb; op.dbg_dtype = 1; op.dbg_bytes = (size_t)rows * cols * sizeof(T); }
@@ -628,6 +710,7 @@ struct Engine : EngineBase {
   }
 
   // One [Resnet, Modulation, Inject, Attention?, CrossAttention?] group.  `cur` = stats of the tensor in bufA[d].
+  void* item_t_out = nullptr;   // where the last built item left the operand-precision copy of its output
   int build_item(int d, int s, int i, double*& cur, bool want_t, bool want_stats) {
     const int64_t B = plan.B;
     const int Beff = plan.cfg_on ? 2 * (int)B : (int)B;
@@ -637,66 +720,96 @@ struct Engine : EngineBase {
     T* T1 = at<T>(plan.lay.T1[d]);
     T* T2 = at<T>(plan.lay.T2[d]);
     const float* xb = I.has_xattn ? at<float>(plan.lay.xbias) + I.xb_off : nullptr;
-    auto base = [&](int kind) { Op o; o.kind = kind; o.depth = d; o.stack = s; o.item = i; o.L = L; o.C = C; o.gs = gs; o.B = Beff; return o; };
+    auto base = [&](int kind, const char* ck) { Op o; o.kind = kind; o.depth = d; o.stack = s; o.item = i; o.L = L; o.C = C; o.gs = gs; o.B = Beff; o.ck = ck; return o; };
     const int rows = Beff * L;
-    {  // gn1 + SiLU
-      Op o = base(OP_GN); o.in = A; o.in_is_f32 = 1; o.stats_in = cur; o.w0 = I.gn1_g; o.w1 = I.gn1_b; o.out_t = T1;
-      set_dbg(o, rows, C); plan.ops.push_back(o);
-    }
-    double* sB = new_stats(Beff);
-    if (d == 0) {
-      Op o = base(OP_CONV_C8); o.in = T1; o.w0 = I.c8_w1; o.w1 = I.c8_b1; o.out_t = T2; o.stats_out = sB;
-      set_dbg(o, rows, C); plan.ops.push_back(o);
-    } else {
-      Op o = base(OP_GEMM); o.out_t = T2; o.stats_out = sB;
-      if (!add_gemm(o, I.conv1, T1, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (conv1 d%d)", d);
-      o.gp.gs = gs; set_dbg(o, rows, C); plan.ops.push_back(o);
-    }
-    {  // gn2 + SiLU
-      Op o = base(OP_GN); o.in = T2; o.in_is_f32 = 0; o.stats_in = sB; o.w0 = I.gn2_g; o.w1 = I.gn2_b; o.out_t = T1;
-      set_dbg(o, rows, C); plan.ops.push_back(o);
-    }
-    if (d == 0) {
-      Op o = base(OP_CONV_C8); o.in = T1; o.w0 = I.c8_w2; o.w1 = I.c8_b2; o.resid = A; o.out_r = A;
-      set_dbg(o, rows, C); plan.ops.push_back(o);
-    } else {
-      Op o = base(OP_GEMM); o.resid = A; o.out_r = A;
-      if (!add_gemm(o, I.conv2, T1, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (conv2 d%d)", d);
-      set_dbg(o, rows, C); plan.ops.push_back(o);
-    }
-    {  // Modulation
-      Op o = base(OP_LN); o.in = A; o.out_t = T1; o.out_r = A; o.ft_off = I.mod_off;
-      set_dbg(o, rows, C); plan.ops.push_back(o);
-    }
     const bool last_is_inject = !I.has_attn;
+    double* sB = new_stats(Beff);
     double* sOut = want_stats ? new_stats(Beff) : nullptr;
-    if (d == 0) {
-      Op o = base(OP_INJ_C8); o.in = T1; o.resid = A; o.in2 = at<T>(plan.lay.ctx[d]); o.ctx = ctx; o.w0 = I.c8_wi; o.w1 = I.c8_bi;
-      o.w2 = xb; o.out_r = A; o.out_t = want_t ? T2 : nullptr; o.stats_out = sOut;
-      set_dbg(o, rows, C); plan.ops.push_back(o);
+    item_t_out = T2;
+    if (I.rk1_id >= 0) {
+      // ---- fused path (bf16, C <= 64): two launches per item, every tensor crosses HBM once per launch
+      if constexpr (kBF16) {
+        {  // R1: h = conv1(SiLU(GN1(x))) + b1 -> T2 (bf16) + GroupNorm sums of h
+          Op o = base(OP_RK, "conv1"); o.in = A; o.stats_in = cur; o.stats_out = sB;
+          if (!add_rk(o, I.rk1_id, A, I.rk1_w, L, Beff) || !rk_out_t(o, T2)) return fail(SFB_ERR_CUDA, "tensor map encode failed (rk1 d%d)", d);
+          o.rp.stats_in = cur; o.rp.stats_out = sB; o.rp.gamma = I.gn1_g; o.rp.beta = I.gn1_b; o.rp.bias = I.conv1.bias;
+          o.flops = 2.0 * rows * C * 3.0 * C; o.bytes = (double)rows * C * (4 + 2);
+          set_dbg(o, rows, C); plan.ops.push_back(o);
+        }
+        {  // R2: y = inject(Mod(conv2(SiLU(GN2(h))) + b2 + x)) (+ cross-attention bias) -> bufA in place (+ bf16 copy -> T1)
+          Op o = base(OP_RK, "inject"); o.in = T2; o.stats_in = sB; o.ft_off = I.mod_off; o.ctx = ctx;
+          if (!add_rk(o, I.rk2_id, T2, I.rk2_w, L, Beff) || !rk_out_r(o, A, true)) return fail(SFB_ERR_CUDA, "tensor map encode failed (rk2 d%d)", d);
+          if (last_is_inject && want_t) { if (!rk_out_t(o, T1)) return fail(SFB_ERR_CUDA, "tensor map encode failed (rk2 d%d)", d); item_t_out = T1; }
+          if (!make_tmap3<__nv_bfloat16>(&o.rp.tmC, at<T>(plan.lay.ctx[d]), ctx, L, (int)B, ctx, 128, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return fail(SFB_ERR_CUDA, "tensor map encode failed (rk2 ctx d%d)", d);
+          o.rp.ctx_bmod = (int)B; o.rp.ctx_ch = ctx;
+          o.rp.stats_in = sB; o.rp.gamma = I.gn2_g; o.rp.beta = I.gn2_b; o.rp.bias = I.conv2.bias; o.rp.bias2 = I.inject.bias;
+          if (last_is_inject) {
+            o.stats_out = sOut; o.rp.stats_out = sOut;
+            if (xb) { o.rp.rowvec = xb; o.rp.rowvec_stride = XB_total; }
+          }
+          o.flops = 2.0 * rows * C * (3.0 * C + C + ctx); o.bytes = (double)rows * (C * (2 + 4 + 4 + (o.rp.has_out_t ? 2 : 0)) + ctx * 2);
+          set_dbg(o, rows, C); plan.ops.push_back(o);
+        }
+      }
     } else {
-      Op o = base(OP_GEMM); o.resid = A; o.out_r = A;
-      o.out_t = (last_is_inject && want_t) ? T2 : nullptr;
-      o.stats_out = last_is_inject ? sOut : nullptr;
-      if (!add_gemm(o, I.inject, T1, C, L, Beff, at<T>(plan.lay.ctx[d]), (int)B)) return fail(SFB_ERR_CUDA, "tensor map encode failed (inject d%d)", d);
-      o.gp.gs = gs;
-      if (last_is_inject && xb) { o.gp.rowvec = xb; o.gp.rowvec_stride = XB_total; }
-      set_dbg(o, rows, C); plan.ops.push_back(o);
+      {  // gn1 + SiLU
+        Op o = base(OP_GN, "gn1"); o.in = A; o.in_is_f32 = 1; o.stats_in = cur; o.w0 = I.gn1_g; o.w1 = I.gn1_b; o.out_t = T1;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+      if (d == 0) {
+        Op o = base(OP_CONV_C8, "conv1"); o.in = T1; o.w0 = I.c8_w1; o.w1 = I.c8_b1; o.out_t = T2; o.stats_out = sB;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      } else {
+        Op o = base(OP_GEMM, "conv1"); o.out_t = T2; o.stats_out = sB;
+        if (!add_gemm(o, I.conv1, T1, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (conv1 d%d)", d);
+        o.gp.gs = gs; set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+      {  // gn2 + SiLU
+        Op o = base(OP_GN, "gn2"); o.in = T2; o.in_is_f32 = 0; o.stats_in = sB; o.w0 = I.gn2_g; o.w1 = I.gn2_b; o.out_t = T1;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+      if (d == 0) {
+        Op o = base(OP_CONV_C8, "conv2"); o.in = T1; o.w0 = I.c8_w2; o.w1 = I.c8_b2; o.resid = A; o.out_r = A;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      } else {
+        Op o = base(OP_GEMM, "conv2"); o.resid = A; o.out_r = A;
+        if (!add_gemm(o, I.conv2, T1, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (conv2 d%d)", d);
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+      {  // Modulation
+        Op o = base(OP_LN, "mod"); o.in = A; o.out_t = T1; o.out_r = A; o.ft_off = I.mod_off;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+      if (d == 0) {
+        Op o = base(OP_INJ_C8, "inject"); o.in = T1; o.resid = A; o.in2 = at<T>(plan.lay.ctx[d]); o.ctx = ctx; o.w0 = I.c8_wi; o.w1 = I.c8_bi;
+        o.w2 = xb; o.out_r = A; o.out_t = want_t ? T2 : nullptr; o.stats_out = sOut;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      } else {
+        Op o = base(OP_GEMM, "inject"); o.resid = A; o.out_r = A;
+        o.out_t = (last_is_inject && want_t) ? T2 : nullptr;
+        o.stats_out = last_is_inject ? sOut : nullptr;
+        if (!add_gemm(o, I.inject, T1, C, L, Beff, at<T>(plan.lay.ctx[d]), (int)B)) return fail(SFB_ERR_CUDA, "tensor map encode failed (inject d%d)", d);
+        o.gp.gs = gs;
+        if (last_is_inject && xb) { o.gp.rowvec = xb; o.gp.rowvec_stride = XB_total; }
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
     }
     if (I.has_attn) {
       T* QKV = at<T>(plan.lay.qkv[d]);
       T* O = at<T>(plan.lay.o[d]);
+      item_t_out = T2;
       {  // pre-norm (affine folded into W_qkv)
-        Op o = base(OP_LN); o.in = A; o.out_t = T1; o.out_r = nullptr; o.ft_off = -1;
+        Op o = base(OP_LN, "attn_ln"); o.in = A; o.out_t = T1; o.out_r = nullptr; o.ft_off = -1;
         set_dbg(o, rows, C); plan.ops.push_back(o);
       }
       {
-        Op o = base(OP_GEMM); o.out_t = QKV;
+        Op o = base(OP_GEMM, "qkv"); o.out_t = QKV;
         if (!add_gemm(o, I.qkv, T1, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (qkv d%d)", d);
         set_dbg(o, rows, 1536); plan.ops.push_back(o);
       }
       {
-        Op o = base(OP_ATTN); o.in = QKV; o.out_t = O;
+        Op o = base(OP_ATTN, "attn"); o.in = QKV; o.out_t = O;
         constexpr int AE = ElemTraits<T>::kAtomElems;
         if (!make_tmap3<T>(&o.ap.tmQ, QKV, 1536, L, Beff, AE, 128) ||
             !make_tmap3<T>(&o.ap.tmKV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV) ||
@@ -707,7 +820,7 @@ struct Engine : EngineBase {
         set_dbg(o, rows, 512); plan.ops.push_back(o);
       }
       {
-        Op o = base(OP_GEMM); o.resid = A; o.out_r = A; o.out_t = want_t ? T2 : nullptr; o.stats_out = sOut;
+        Op o = base(OP_GEMM, "out"); o.resid = A; o.out_r = A; o.out_t = want_t ? T2 : nullptr; o.stats_out = sOut;
         if (!add_gemm(o, I.out, O, 512, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (to_out d%d)", d);
         o.gp.gs = gs;
         if (xb) { o.gp.rowvec = xb; o.gp.rowvec_stride = XB_total; }
@@ -726,13 +839,22 @@ struct Engine : EngineBase {
     const DepthW& W = dw[d];
     float* A = at<float>(plan.lay.bufA[d]);
     double* cur = new_stats(Beff);
+    const void* down_in = item_t_out;   // operand copy of the previous depth's last down-stack item
     if (d == 0) {
-      Op o; o.kind = OP_D0_DOWN; o.depth = 0; o.stack = 2; o.L = L; o.C = C; o.B = Beff; o.w0 = W.c8_dw; o.w1 = W.c8_db;
+      Op o; o.kind = OP_D0_DOWN; o.depth = 0; o.stack = 2; o.L = L; o.C = C; o.B = Beff; o.w0 = W.c8_dw; o.w1 = W.c8_db; o.ck = "down";
       o.out_r = A; o.stats_out = cur; set_dbg(o, Beff * L, C); plan.ops.push_back(o);
+    } else if (W.rk_down_id >= 0) {
+      const int Cin = cfg.channels[d - 1];
+      Op o; o.depth = d; o.stack = 2; o.stats_out = cur; o.ck = "down"; o.in = down_in;
+      if (!add_rk(o, W.rk_down_id, down_in, W.rk_down_w, L, Beff) || !rk_out_r(o, A, false))
+        return fail(SFB_ERR_CUDA, "tensor map encode failed (rk down d%d)", d);
+      o.rp.stats_out = cur; o.rp.bias = W.down.bias;
+      o.flops = 2.0 * Beff * L * C * (double)f * Cin; o.bytes = (double)Beff * L * (f * Cin * 2 + C * 4);
+      set_dbg(o, Beff * L, C); plan.ops.push_back(o);
     } else {
       const int Cin = cfg.channels[d - 1];
-      Op o; o.depth = d; o.stack = 2; o.out_r = A; o.stats_out = cur;
-      if (!add_gemm(o, W.down, at<T>(plan.lay.T2[d - 1]), f * Cin, L, Beff, nullptr, 0))
+      Op o; o.depth = d; o.stack = 2; o.out_r = A; o.stats_out = cur; o.ck = "down";
+      if (!add_gemm(o, W.down, down_in, f * Cin, L, Beff, nullptr, 0))
         return fail(SFB_ERR_CUDA, "tensor map encode failed (down d%d)", d);
       o.gp.gs = C / 8; set_dbg(o, Beff * L, C); plan.ops.push_back(o);
     }
@@ -754,17 +876,26 @@ struct Engine : EngineBase {
       if (rc) return rc;
     }
     if (d == 0) {
-      Op o; o.kind = OP_D0_UP; o.depth = 0; o.stack = 2; o.L = L; o.C = C; o.B = Beff; o.in = at<T>(plan.lay.T2[0]);
+      Op o; o.kind = OP_D0_UP; o.depth = 0; o.stack = 2; o.L = L; o.C = C; o.B = Beff; o.in = item_t_out; o.ck = "up";
       o.w0 = W.c8_uw; o.fscalar = W.c8_ub; o.taps = W.up_taps; o.ft_off = W.skip_off; o.out_r = at<float>(plan.lay.veff);
       set_dbg(o, Beff, L); plan.ops.push_back(o);
     } else {
       const int Cin = cfg.channels[d - 1];
       float* Ap = at<float>(plan.lay.bufA[d - 1]);
       double* so = new_stats(Beff);
-      Op o; o.depth = d; o.stack = 3; o.resid = Ap; o.out_r = Ap; o.stats_out = so; o.ft_off = W.skip_off;
-      if (!add_gemm(o, W.up, at<T>(plan.lay.T2[d]), C, L, Beff, nullptr, 0))
-        return fail(SFB_ERR_CUDA, "tensor map encode failed (up d%d)", d);
-      o.gp.gs = Cin / 8; set_dbg(o, Beff * Ld(plan.L, d - 1), Cin); plan.ops.push_back(o);
+      if (W.rk_up_id >= 0) {
+        Op o; o.depth = d; o.stack = 3; o.stats_out = so; o.ft_off = W.skip_off; o.ck = "up"; o.in = item_t_out;
+        if (!add_rk(o, W.rk_up_id, item_t_out, W.rk_up_w, L, Beff) || !rk_out_r(o, Ap, true))
+          return fail(SFB_ERR_CUDA, "tensor map encode failed (rk up d%d)", d);
+        o.rp.stats_out = so; o.rp.bias = W.up.bias;
+        o.flops = 2.0 * Beff * L * (double)W.up.N * W.up.taps * C; o.bytes = (double)Beff * L * (C * 2 + W.up.N * 8);
+        set_dbg(o, Beff * Ld(plan.L, d - 1), Cin); plan.ops.push_back(o);
+      } else {
+        Op o; o.depth = d; o.stack = 3; o.resid = Ap; o.out_r = Ap; o.stats_out = so; o.ft_off = W.skip_off; o.ck = "up";
+        if (!add_gemm(o, W.up, item_t_out, C, L, Beff, nullptr, 0))
+          return fail(SFB_ERR_CUDA, "tensor map encode failed (up d%d)", d);
+        o.gp.gs = Cin / 8; set_dbg(o, Beff * Ld(plan.L, d - 1), Cin); plan.ops.push_back(o);
+      }
       inner_out_stats = so;
     }
     return SFB_OK;
@@ -788,6 +919,9 @@ struct Engine : EngineBase {
         flops = 2.0 * rows * o.gp.N * K;
         bytes = rows * K / o.gp.taps * sizeof(T) + rows * o.gp.N * ((o.gp.resid ? 4 : 0) + (o.gp.out_r ? 4 : 0) + (o.gp.out_t ? sizeof(T) : 0)) +
                 (double)o.gp.taps * o.gp.N * (K / o.gp.taps) * sizeof(T);
+      } else if (o.kind == OP_RK) {
+        flops = o.flops;
+        bytes = o.bytes;
       } else if (o.kind == OP_ATTN) {
         flops = 4.0 * (double)o.B * 8 * (double)o.L * o.L * 64;
         bytes = rows * (1536 + 512) * sizeof(T);
@@ -844,8 +978,8 @@ struct Engine : EngineBase {
   int op_info(int i, char* buf, int len) override {
     if (i < 0 || i >= (int)plan.ops.size()) return fail(SFB_ERR_INVALID, "op index out of range");
     const Op& o = plan.ops[i];
-    snprintf(buf, len, "%s %d %d %d %zu %zu %d %d %d", kOpNames[o.kind], o.depth, o.stack, o.item, o.dbg_off, o.dbg_bytes,
-             o.dbg_rows, o.dbg_cols, o.dbg_dtype);
+    snprintf(buf, len, "%s %d %d %d %zu %zu %d %d %d %s", kOpNames[o.kind], o.depth, o.stack, o.item, o.dbg_off, o.dbg_bytes,
+             o.dbg_rows, o.dbg_cols, o.dbg_dtype, o.ck[0] ? o.ck : "-");
     return SFB_OK;
   }
 
@@ -921,6 +1055,17 @@ struct Engine : EngineBase {
             launch_gemm<T>(p, o.BN, o.B, st);
           } else {
             launch_gemm<T>(o.gp, o.BN, o.B, st);
+          }
+          break;
+        }
+        case OP_RK: {
+          if constexpr (kBF16) {
+            RkParams p = o.rp;
+            if (o.ft_off >= 0) {
+              if (rk_key(o.rk_id).EPI >= 1) { p.mod = sc.frow + o.ft_off; p.mod_bstride = sc.bstride; p.mod_bmod = sc.bmod; }
+              else { p.colscale = sc.frow + o.ft_off; p.cs_bstride = sc.bstride; p.cs_bmod = sc.bmod; }
+            }
+            rk_launch(o.rk_id, p, num_sms(), st);
           }
           break;
         }

@@ -214,9 +214,9 @@ class UNetV0:
         buf = C.create_string_buffer(256)
         for i in range(n):
             self._check(self._lib.sfb_dbg_op_info(self._h, i, buf, 256))
-            kind, depth, stack, item, off, nbytes, rows, cols, dt = buf.value.decode().split()
+            kind, depth, stack, item, off, nbytes, rows, cols, dt, ck = buf.value.decode().split()
             ops.append(dict(kind=kind, depth=int(depth), stack=int(stack), item=int(item), off=int(off),
-                            nbytes=int(nbytes), rows=int(rows), cols=int(cols), dtype=int(dt)))
+                            nbytes=int(nbytes), rows=int(rows), cols=int(cols), dtype=int(dt), ck=ck))
         return ops, ws
 
     def profile(self, enable: bool):

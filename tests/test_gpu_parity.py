@@ -122,19 +122,26 @@ def test_unet_layerwise_and_output(dev, precision, upsample_mode, scale):
     assert rel_l2(v, v_ref) < TOL_V[precision]
     assert rel_l2(v - x, v_ref - x) < 10 * TOL_V[precision]
     ops, ws = net.debug_ops(B, L, int(scale != 1.0))
-    assert len(ops) == len(tr)
     tdt = torch.float32 if precision == "fp32" else torch.bfloat16
     pad = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
+    if precision == "bf16":
+        assert any(op["kind"] == "rk" for op in ops), "the fused resident-weight kernels must be on the bf16 path"
+    j = 0
     try:
-        for i, (op, (kinds, ref)) in enumerate(zip(ops, tr)):
-            assert op["kind"] in kinds.split("|"), (i, op, kinds)
+        for i, op in enumerate(ops):
+            ck = "up0" if (op["ck"] == "up" and op["kind"] == "d0_up") else op["ck"]
+            while j < len(tr) and tr[j][0] != ck:      # checkpoints a fused op never materialises
+                j += 1
+            assert j < len(tr), (i, op)
+            ref = tr[j][1]
+            j += 1
             net.debug_set_op_limit(i + 1)
             net(x, t, embedding=e, embedding_scale=scale, channels=ch)
             torch.cuda.synchronize()
             raw = ws[pad + op["off"]: pad + op["off"] + op["nbytes"]]
             got = raw.view(torch.float32 if op["dtype"] == 0 else tdt).reshape(op["rows"], op["cols"]).float()
             err = rel_l2(got, ref.reshape(op["rows"], op["cols"]))
-            assert err < TOL_OP[precision], (i, op["kind"], op["depth"], err)
+            assert err < TOL_OP[precision], (i, op["kind"], op["ck"], op["depth"], err)
     finally:
         net.debug_set_op_limit(-1)
 

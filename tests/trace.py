@@ -1,6 +1,7 @@
-"""Re-runs the oracle U-Net op by op in the order of the CUDA execution plan, so every plan op of
-``libsyncfusion_b200.so`` can be compared with the oracle tensor it must reproduce (layer-wise parity,
-SURVEY.md 8(c)-6).  Pure oracle math; ``test_oracle.py`` checks that the trace's final tensor equals
+"""Re-runs the oracle U-Net op by op and records a named checkpoint after every sub-step (down, gn1, conv1, gn2,
+conv2, mod, inject, attn_ln, qkv, attn, out, up), so every plan op of ``libsyncfusion_b200.so`` can be compared with
+the oracle tensor it must reproduce (layer-wise parity).  Fused plan ops name the checkpoint their
+output equals; the checkpoints a fused op never materialises are skipped.  Pure oracle math; ``test_oracle.py`` checks that the trace's final tensor equals
 ``UNetV0.forward``."""
 from __future__ import annotations
 
@@ -16,23 +17,23 @@ def _nlc(t):                       # [B, C, L] -> [B*L, C]
 
 def _trace_item(it, x, features, embedding, channels, out: List[Tuple[str, torch.Tensor]]):
     r = it.resnet
-    t1 = F.silu(r.gn1(x)); out.append(("gn_silu", _nlc(t1)))
-    t2 = r.conv1(t1); out.append(("gemm|conv3_c8", _nlc(t2)))
-    t3 = F.silu(r.gn2(t2)); out.append(("gn_silu", _nlc(t3)))
-    h = r.conv2(t3) + x; out.append(("gemm|conv3_c8", _nlc(h)))
-    m = it.mod(h, features); out.append(("ln", _nlc(m)))
+    t1 = F.silu(r.gn1(x)); out.append(("gn1", _nlc(t1)))
+    t2 = r.conv1(t1); out.append(("conv1", _nlc(t2)))
+    t3 = F.silu(r.gn2(t2)); out.append(("gn2", _nlc(t3)))
+    h = r.conv2(t3) + x; out.append(("conv2", _nlc(h)))
+    m = it.mod(h, features); out.append(("mod", _nlc(m)))
     i = it.inject(m, channels)
     if it.attn is None:
         if it.xattn is not None:
             i = it.xattn(i, embedding)
-        out.append(("gemm|inject_c8", _nlc(i)))
+        out.append(("inject", _nlc(i)))
         return i
-    out.append(("gemm", _nlc(i)))
+    out.append(("inject", _nlc(i)))
     a = it.attn.attn
     xt = i.transpose(1, 2)
-    out.append(("ln", F.layer_norm(xt, (xt.shape[-1],)).reshape(-1, xt.shape[-1])))
+    out.append(("attn_ln", F.layer_norm(xt, (xt.shape[-1],)).reshape(-1, xt.shape[-1])))
     q = a.to_q(a.norm(xt)); kv = a.to_kv(a.norm_ctx(xt))
-    out.append(("gemm", torch.cat([q, kv], dim=-1).reshape(-1, q.shape[-1] + kv.shape[-1])))
+    out.append(("qkv", torch.cat([q, kv], dim=-1).reshape(-1, q.shape[-1] + kv.shape[-1])))
     k, v = kv.chunk(2, dim=-1)
     b, n, _ = q.shape
     hq, hk, hv = (t.reshape(b, n, a.num_heads, -1).transpose(1, 2) for t in (q, k, v))
@@ -41,12 +42,12 @@ def _trace_item(it, x, features, embedding, channels, out: List[Tuple[str, torch
     y = it.attn(i)
     if it.xattn is not None:
         y = it.xattn(y, embedding)
-    out.append(("gemm", _nlc(y)))
+    out.append(("out", _nlc(y)))
     return y
 
 
 def _trace_block(blk, x, features, embedding, channels, out, depth=0):
-    y = blk.down(x); out.append(("d0_down" if depth == 0 else "gemm", _nlc(y)))
+    y = blk.down(x); out.append(("down", _nlc(y)))
     for it in blk.items_down:
         y = _trace_item(it, y, features, embedding, channels, out)
     if blk.inner is not None:
@@ -56,7 +57,7 @@ def _trace_block(blk, x, features, embedding, channels, out, depth=0):
     y = blk.up(y)
     s = blk.skip(F.silu(features))[:, :, None]
     r = x + s * y
-    out.append(("d0_up", r.reshape(r.shape[0], -1)) if depth == 0 else ("gemm", _nlc(r)))
+    out.append(("up0", r.reshape(r.shape[0], -1)) if depth == 0 else ("up", _nlc(r)))
     return r
 
 
@@ -75,9 +76,6 @@ def trace_unet(net, x, time, embedding, channels, embedding_scale=1.0):
     v2 = _trace_block(net.blocks, x, features, mask, channels, o2)
     out = []
     for (k, a), (_, c) in zip(o1, o2):
-        if k == "d0_up":
-            out.append((k, torch.cat([a, c], dim=0)))
-        else:
-            # rows are clip-major inside each branch: [B*L, C] cond then [B*L, C] uncond
-            out.append((k, torch.cat([a, c], dim=0)))
+        # rows are clip-major inside each branch: [B*L, C] cond then [B*L, C] uncond
+        out.append((k, torch.cat([a, c], dim=0)))
     return out, v2 + (v1 - v2) * embedding_scale
