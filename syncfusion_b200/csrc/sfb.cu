@@ -21,6 +21,7 @@
 #include "gemm_tc.cuh"
 #include "prepare.cuh"
 #include "rk_tc.cuh"
+#include "sk_tc.cuh"
 
 using namespace sfb;
 
@@ -129,8 +130,8 @@ struct DepthW {
   int skip_off = 0;
 };
 
-enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN, OP_RK };
-const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn", "rk"};
+enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN, OP_RK, OP_SK };
+const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn", "rk", "sk"};
 
 struct EngineBase {
   sfb_unet_config cfg;
@@ -249,7 +250,8 @@ struct Engine : EngineBase {
   float *t_w = nullptr, *t_lw = nullptr, *t_lb = nullptr, *t_mw = nullptr, *t_mb = nullptr, *fixed_emb = nullptr;
   float *ft_w = nullptr, *ft_b = nullptr;   // concatenated Linear(SiLU(features)) weights [F_total][MF]
   int F_total = 0, XB_total = 0, n_gn = 0;
-  bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aid: force the unfused generic path everywhere
+  bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aids: force the unfused generic path
+  bool no_sk = getenv("SFB_NO_SK") != nullptr;
 
   struct Op {
     int kind = 0, depth = 0, stack = 0, item = 0;
@@ -268,6 +270,8 @@ struct Engine : EngineBase {
     AttnParams<T> ap;
     RkParams rp;
     int rk_id = -1;
+    SkParams sp;
+    int sk_id = -1, sk_ft_is_mod = 0;
     double flops = 0, bytes = 0;   // algorithmic work of an OP_RK op (set at build time)
     const char* ck = "";           // oracle-trace checkpoint this op's output equals (tests/trace.py)
     int BN = 0;
@@ -277,6 +281,7 @@ struct Engine : EngineBase {
   struct WsLayout {
     size_t sigma, embrows, tmp1, tmp2, fourier, h1, h2, feat, ftable, xbias, stats, stats_bytes, veff, xstate, total;
     size_t ctx[SFB_MAX_DEPTH], bufA[SFB_MAX_DEPTH], T1[SFB_MAX_DEPTH], T2[SFB_MAX_DEPTH], qkv[SFB_MAX_DEPTH], o[SFB_MAX_DEPTH];
+    size_t rs1[SFB_MAX_DEPTH], rs2[SFB_MAX_DEPTH];   // per-position LayerNorm partial sums [rows, parts <= 8, 2] (sk path)
   };
   struct Plan {
     int64_t B = 0, L = 0;
@@ -361,6 +366,7 @@ struct Engine : EngineBase {
     if (c.attentions[0]) return fail(SFB_ERR_UNSUPPORTED, "self-attention at depth 0 unsupported");
     if (set_kernel_attrs<T>() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (kBF16 && rk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (rk) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (kBF16 && sk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (sk) failed: %s", cudaGetErrorString(cudaGetLastError()));
 
     // time conditioning (A.3)
     t_w = upload_f(get("time.weights", {128}));
@@ -632,6 +638,11 @@ struct Engine : EngineBase {
       w.bufA[d] = take((size_t)Beff * ld * C * 4);
       w.T1[d] = take((size_t)Beff * ld * C * sizeof(T));
       w.T2[d] = take((size_t)Beff * ld * C * sizeof(T));
+      w.rs1[d] = w.rs2[d] = 0;
+      if (kBF16 && C % 128 == 0) {
+        w.rs1[d] = take((size_t)Beff * ld * 8 * 2 * 4);
+        w.rs2[d] = take((size_t)Beff * ld * 8 * 2 * 4);
+      }
       if (cfg.attentions[d]) {
         w.qkv[d] = take((size_t)Beff * ld * 1536 * sizeof(T));
         w.o[d] = take((size_t)Beff * ld * 512 * sizeof(T));
@@ -703,10 +714,141 @@ struct Engine : EngineBase {
     op.out_t = ptr; op.rp.has_out_t = 1;
     return make_tmap3<__nv_bfloat16>(&op.rp.tmT, ptr, k.N, op.L, op.B, 64, 128);
   }
+  // Streaming-K fused GEMM (sk_tc.cuh).  gs_out: GroupNorm group size of the output statistics (0: none).
+  bool sk_ok(const GemmW& g) const { return kBF16 && !no_sk && g.N % 128 == 0 && g.K1 % 64 == 0 && g.w != nullptr; }
+  bool add_sk(Op& op, const GemmW& g, const void* a1, int L, int Beff, const void* a2, int B2, int gs_out) {
+    const int BN = g.N % 256 == 0 ? 256 : 128;
+    int id = sk_find(BN, gs_out > 0 ? gs_out : (BN == 256 ? 32 : 16));
+    if (id < 0) return false;
+    op.kind = OP_SK; op.sk_id = id; op.B = Beff; op.L = L; op.C = g.N; op.k2 = g.K2; op.BN = BN;
+    SkParams& p = op.sp;
+    memset(&p, 0, sizeof p);
+    if (!make_tmap3<__nv_bfloat16>(&p.tmA1, a1, g.K1, L, Beff, 64, g.taps == 3 ? 136 : 128)) return false;
+    if (g.K2 > 0) { if (!make_tmap3<__nv_bfloat16>(&p.tmA2, a2, g.K2, L, B2, 64, 128)) return false; }
+    else p.tmA2 = p.tmA1;
+    if (!make_tmap2<__nv_bfloat16>(&p.tmW, g.w, (uint64_t)(g.K1 + g.K2), (uint64_t)g.taps * g.N, 64, BN)) return false;
+    p.tmR = p.tmA1; p.tmT = p.tmA1;
+    p.L = L; p.tiles_per_clip = (L + 127) / 128; p.N = g.N; p.n_tiles = g.N / BN;
+    p.total_tiles = Beff * p.tiles_per_clip * p.n_tiles;
+    p.taps = g.taps; p.k1_chunks = g.K1 / 64; p.k2_chunks = (g.K2 + 63) / 64; p.K1 = g.K1; p.a2_bmod = B2 > 0 ? B2 : 1;
+    p.bias = g.bias; p.bias_mod = g.bias_mod > 0 ? g.bias_mod : g.N;
+    p.cs_bmod = 1; p.mod_bmod = 1; p.rs_parts = 1;
+    p.eps = 1e-5f;
+    op.flops = 2.0 * Beff * L * (double)g.N * ((double)g.taps * g.K1 + g.K2);
+    op.bytes = (double)Beff * L * (g.K1 + g.K2) * 2;
+    return true;
+  }
+  bool sk_out_r(Op& op, float* ptr, int resid_mode) {
+    op.out_r = ptr; op.sp.has_out_r = 1; op.sp.resid_mode = resid_mode;
+    if (resid_mode) op.resid = ptr;
+    op.bytes += (double)op.B * op.L * op.sp.N * (resid_mode ? 8 : 4);
+    return make_tmap3<float>(&op.sp.tmR, ptr, op.sp.N, op.L, op.B, 32, 128);
+  }
+  bool sk_out_t(Op& op, void* ptr) {
+    op.out_t = ptr; op.sp.has_out_t = 1;
+    op.bytes += (double)op.B * op.L * op.sp.N * 2;
+    return make_tmap3<__nv_bfloat16>(&op.sp.tmT, ptr, op.sp.N, op.L, op.B, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+  }
   void set_dbg(Op& op, int rows, int cols) {
     if (op.out_r) { op.dbg_off = (uint8_t*)op.out_r - wsb; op.dbg_dtype = 0; op.dbg_bytes = (size_t)rows * cols * 4; }
     else { op.dbg_off = (uint8_t*)op.out_t - wsb; op.dbg_dtype = 1; op.dbg_bytes = (size_t)rows * cols * sizeof(T); }
     op.dbg_rows = rows; op.dbg_cols = cols;
+  }
+
+  // ---- streaming-K fused path (bf16, C % 128 == 0): every norm is folded into a GEMM prologue / epilogue -------------
+  void* xt_cur[SFB_MAX_DEPTH] = {};   // bf16 copy of the tensor currently in bufA[d] (written by whoever produced it)
+  bool depth_sk(int d) const {
+    if (!kBF16 || no_sk || d == 0 || cfg.channels[d] % 128) return false;
+    if (!sk_ok(dw[d].down)) return false;
+    for (int s = 0; s < 2; ++s)
+      for (const ItemW& I : dw[d].items[s]) {
+        if (!sk_ok(I.conv1) || !sk_ok(I.conv2) || !sk_ok(I.inject)) return false;
+        if (I.has_attn && (!sk_ok(I.qkv) || !sk_ok(I.out))) return false;
+      }
+    if (d + 1 < cfg.depth && !sk_ok(dw[d + 1].up)) return false;
+    return true;
+  }
+  int build_item_sk(int d, int s, int i, double*& cur, bool want_stats) {
+    const int64_t B = plan.B;
+    const int Beff = plan.cfg_on ? 2 * (int)B : (int)B;
+    const int C = cfg.channels[d], L = Ld(plan.L, d), gs = C / 8;
+    const ItemW& I = dw[d].items[s][i];
+    float* A = at<float>(plan.lay.bufA[d]);
+    T* T1 = at<T>(plan.lay.T1[d]);
+    T* T2 = at<T>(plan.lay.T2[d]);
+    float* RS1 = at<float>(plan.lay.rs1[d]);
+    float* RS2 = at<float>(plan.lay.rs2[d]);
+    void* P0 = xt_cur[d];
+    void* P1 = (P0 == (void*)T1) ? (void*)T2 : (void*)T1;
+    const float* xb = I.has_xattn ? at<float>(plan.lay.xbias) + I.xb_off : nullptr;
+    auto base = [&](const char* ck) { Op o; o.kind = OP_SK; o.depth = d; o.stack = s; o.item = i; o.L = L; o.C = C; o.gs = gs; o.B = Beff; o.ck = ck; return o; };
+    const int rows = Beff * L;
+    double* sB = new_stats(Beff);
+    double* sOut = want_stats ? new_stats(Beff) : nullptr;
+    const char* err_fmt = "tensor map encode failed (sk %s d%d)";
+    {  // conv1: h = conv3(SiLU(GN1(x))) + b  ->  P1 (bf16) + GroupNorm sums of h
+      Op o = base("conv1"); o.in = P0; o.stats_in = cur; o.stats_out = sB;
+      if (!add_sk(o, I.conv1, P0, L, Beff, nullptr, 0, gs) || !sk_out_t(o, P1)) return fail(SFB_ERR_CUDA, err_fmt, "conv1", d);
+      o.sp.xf = 1; o.sp.stats_in = cur; o.sp.gamma = I.gn1_g; o.sp.beta = I.gn1_b; o.sp.stats_out = sB;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    int parts1;
+    {  // conv2: r = conv3(SiLU(GN2(h))) + b + x  ->  bufA (fp32), P0 (bf16), per-position LayerNorm sums of r
+      Op o = base("conv2"); o.in = P1; o.stats_in = sB;
+      if (!add_sk(o, I.conv2, P1, L, Beff, nullptr, 0, 0) || !sk_out_r(o, A, 1) || !sk_out_t(o, P0)) return fail(SFB_ERR_CUDA, err_fmt, "conv2", d);
+      o.sp.xf = 1; o.sp.stats_in = sB; o.sp.gamma = I.gn2_g; o.sp.beta = I.gn2_b; o.sp.rowstats_out = RS1;
+      parts1 = o.sp.n_tiles;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    const bool last_is_inject = !I.has_attn;
+    int parts2;
+    {  // inject: i = W [Mod(LN(r)) | ctx] + b + Mod(LN(r)) (+ cross-attention bias)  ->  bufA (fp32), P1 (bf16)
+      Op o = base("inject"); o.in = P0; o.ft_off = I.mod_off; o.sk_ft_is_mod = 1; o.ctx = cfg.context_channels[d];
+      if (!add_sk(o, I.inject, P0, L, Beff, at<T>(plan.lay.ctx[d]), (int)B, last_is_inject && want_stats ? gs : 0) ||
+          !sk_out_r(o, A, 2) || !sk_out_t(o, P1)) return fail(SFB_ERR_CUDA, err_fmt, "inject", d);
+      o.sp.xf = 2; o.sp.rowstats_in = RS1; o.sp.rs_parts = parts1;
+      if (last_is_inject) {
+        o.stats_out = sOut; o.sp.stats_out = sOut;
+        if (xb) { o.sp.rowvec = xb; o.sp.rowvec_stride = XB_total; }
+      } else {
+        o.sp.rowstats_out = RS2;
+      }
+      parts2 = o.sp.n_tiles;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    xt_cur[d] = P1;
+    if (I.has_attn) {
+      T* QKV = at<T>(plan.lay.qkv[d]);
+      T* O = at<T>(plan.lay.o[d]);
+      {  // fused pre-norm + QKV projection (both LayerNorm affines are folded into W_qkv)
+        Op o = base("qkv"); o.in = P1;
+        if (!add_sk(o, I.qkv, P1, L, Beff, nullptr, 0, 0) || !sk_out_t(o, QKV)) return fail(SFB_ERR_CUDA, err_fmt, "qkv", d);
+        o.sp.xf = 2; o.sp.rowstats_in = RS2; o.sp.rs_parts = parts2;
+        set_dbg(o, rows, 1536); plan.ops.push_back(o);
+      }
+      {
+        Op o; o.kind = OP_ATTN; o.depth = d; o.stack = s; o.item = i; o.L = L; o.C = C; o.gs = gs; o.B = Beff; o.ck = "attn"; o.in = QKV; o.out_t = O;
+        constexpr int AE = ElemTraits<T>::kAtomElems;
+        if (!make_tmap3<T>(&o.ap.tmQ, QKV, 1536, L, Beff, AE, 128) ||
+            !make_tmap3<T>(&o.ap.tmKV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV) ||
+            !make_tmap3<T>(&o.ap.tmV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV,
+                           sizeof(T) == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+          return fail(SFB_ERR_CUDA, "tensor map encode failed (attention d%d)", d);
+        o.ap.out = O; o.ap.n_tokens = L; o.ap.scale_log2 = 1.4426950408889634f / 8.0f;
+        set_dbg(o, rows, 512); plan.ops.push_back(o);
+      }
+      {  // out projection + residual (+ cross-attention bias)  ->  bufA (fp32), P0 (bf16), GroupNorm sums
+        Op o = base("out"); o.in = O; o.stats_out = sOut;
+        if (!add_sk(o, I.out, O, L, Beff, nullptr, 0, want_stats ? gs : 0) || !sk_out_r(o, A, 1) || !sk_out_t(o, P0)) return fail(SFB_ERR_CUDA, err_fmt, "out", d);
+        o.sp.stats_out = sOut;
+        if (xb) { o.sp.rowvec = xb; o.sp.rowvec_stride = XB_total; }
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+      xt_cur[d] = P0;
+    }
+    item_t_out = xt_cur[d];
+    cur = sOut;
+    return SFB_OK;
   }
 
   // One [Resnet, Modulation, Inject, Attention?, CrossAttention?] group.  `cur` = stats of the tensor in bufA[d].
@@ -715,6 +857,7 @@ struct Engine : EngineBase {
     const int64_t B = plan.B;
     const int Beff = plan.cfg_on ? 2 * (int)B : (int)B;
     const int C = cfg.channels[d], L = Ld(plan.L, d), gs = C / 8, ctx = cfg.context_channels[d];
+    if (depth_sk(d)) { if constexpr (kBF16) return build_item_sk(d, s, i, cur, want_stats); }
     const ItemW& I = dw[d].items[s][i];
     float* A = at<float>(plan.lay.bufA[d]);
     T* T1 = at<T>(plan.lay.T1[d]);
@@ -851,6 +994,18 @@ struct Engine : EngineBase {
       o.rp.stats_out = cur; o.rp.bias = W.down.bias;
       o.flops = 2.0 * Beff * L * C * (double)f * Cin; o.bytes = (double)Beff * L * (f * Cin * 2 + C * 4);
       set_dbg(o, Beff * L, C); plan.ops.push_back(o);
+    } else if (sk_ok(W.down)) {
+      Op o; o.depth = d; o.stack = 2; o.stats_out = cur; o.ck = "down"; o.in = down_in;
+      if constexpr (kBF16) {
+        if (!add_sk(o, W.down, down_in, L, Beff, nullptr, 0, C / 8) || !sk_out_r(o, A, 0))
+          return fail(SFB_ERR_CUDA, "tensor map encode failed (sk down d%d)", d);
+        if (depth_sk(d)) {
+          if (!sk_out_t(o, at<T>(plan.lay.T1[d]))) return fail(SFB_ERR_CUDA, "tensor map encode failed (sk down d%d)", d);
+          xt_cur[d] = at<T>(plan.lay.T1[d]);
+        }
+        o.sp.stats_out = cur;
+      }
+      set_dbg(o, Beff * L, C); plan.ops.push_back(o);
     } else {
       const int Cin = cfg.channels[d - 1];
       Op o; o.depth = d; o.stack = 2; o.out_r = A; o.stats_out = cur; o.ck = "down";
@@ -890,6 +1045,18 @@ struct Engine : EngineBase {
         o.rp.stats_out = so; o.rp.bias = W.up.bias;
         o.flops = 2.0 * Beff * L * (double)W.up.N * W.up.taps * C; o.bytes = (double)Beff * L * (C * 2 + W.up.N * 8);
         set_dbg(o, Beff * Ld(plan.L, d - 1), Cin); plan.ops.push_back(o);
+      } else if (sk_ok(W.up)) {
+        Op o; o.depth = d; o.stack = 3; o.stats_out = so; o.ft_off = W.skip_off; o.ck = "up"; o.in = item_t_out;
+        if constexpr (kBF16) {
+          if (!add_sk(o, W.up, item_t_out, L, Beff, nullptr, 0, Cin / 8) || !sk_out_r(o, Ap, 1))
+            return fail(SFB_ERR_CUDA, "tensor map encode failed (sk up d%d)", d);
+          if (depth_sk(d - 1)) {      // the outer depth's up-stack reads the bf16 copy of x
+            if (!sk_out_t(o, at<T>(plan.lay.T1[d - 1]))) return fail(SFB_ERR_CUDA, "tensor map encode failed (sk up d%d)", d);
+            xt_cur[d - 1] = at<T>(plan.lay.T1[d - 1]);
+          }
+          o.sp.stats_out = so;
+        }
+        set_dbg(o, Beff * Ld(plan.L, d - 1), Cin); plan.ops.push_back(o);
       } else {
         Op o; o.depth = d; o.stack = 3; o.resid = Ap; o.out_r = Ap; o.stats_out = so; o.ft_off = W.skip_off; o.ck = "up";
         if (!add_gemm(o, W.up, item_t_out, C, L, Beff, nullptr, 0))
@@ -919,7 +1086,7 @@ struct Engine : EngineBase {
         flops = 2.0 * rows * o.gp.N * K;
         bytes = rows * K / o.gp.taps * sizeof(T) + rows * o.gp.N * ((o.gp.resid ? 4 : 0) + (o.gp.out_r ? 4 : 0) + (o.gp.out_t ? sizeof(T) : 0)) +
                 (double)o.gp.taps * o.gp.N * (K / o.gp.taps) * sizeof(T);
-      } else if (o.kind == OP_RK) {
+      } else if (o.kind == OP_RK || o.kind == OP_SK) {
         flops = o.flops;
         bytes = o.bytes;
       } else if (o.kind == OP_ATTN) {
@@ -1066,6 +1233,17 @@ struct Engine : EngineBase {
               else { p.colscale = sc.frow + o.ft_off; p.cs_bstride = sc.bstride; p.cs_bmod = sc.bmod; }
             }
             rk_launch(o.rk_id, p, num_sms(), st);
+          }
+          break;
+        }
+        case OP_SK: {
+          if constexpr (kBF16) {
+            SkParams p = o.sp;
+            if (o.ft_off >= 0) {
+              if (o.sk_ft_is_mod) { p.mod = sc.frow + o.ft_off; p.mod_bstride = sc.bstride; p.mod_bmod = sc.bmod; }
+              else { p.colscale = sc.frow + o.ft_off; p.cs_bstride = sc.bstride; p.cs_bmod = sc.bmod; }
+            }
+            sk_launch(o.sk_id, p, num_sms(), st);
           }
           break;
         }

@@ -1,0 +1,506 @@
+// Streaming-K fused tcgen05 implicit-GEMM for the tensor-bound depths (C >= 128), bf16 operands.
+//
+//   D[b, l, n] = sum_{tap, k} f(A1)[b, l + tap - pad, k] W[tap N + n, k]  +  sum_k A2[b % m, l, k] W[n, K1 + k]
+//   out        = colscale[n'] (D + bias[n']) + rowvec[b, n'] + g(resid)                    n' = n % bias_mod
+//
+// f = none | GroupNorm(8)+SiLU (ResNet convs, a6) | per-position LayerNorm (x Modulation) (inject a7/a8, QKV pre-norm a9)
+// g = none | identity | LayerNorm/Modulation recomputed in fp32 (InjectChannels adds the MODULATED tensor, which is
+// never stored).  So the GroupNorm / Modulation / pre-norm passes of the reference do not exist as kernels: the
+// statistics they need (fp64 group sums per clip, fp32 row sums per position) are emitted by the PRODUCER's epilogue.
+//
+// Persistent, warp-specialised, 128 x BN output tiles (n fastest), fp32 accumulators double-buffered in TMEM:
+//   warp 0      TMA producer (mainloop): A ring of [136 x 64] bf16 tiles - ONE load per K chunk serves all three conv
+//               taps (row-shifted UMMA descriptors, +128 B per tap) - and a B ring of [BN x 64] weight tiles
+//   warp 1      tcgen05.mma issuer
+//   warp 2      TMA producer (epilogue): residual chunks [128 x 32] fp32 into the R ring
+//   warps 4-7   A transform in place on the landed tile (fence.proxy.async before the MMA sees it)
+//   warps 8-11  epilogue, one accumulator row per thread, 32-column chunks: TMEM -> regs -> math -> fp32 chunk written
+//               IN PLACE over the residual chunk + bf16 chunk -> TMA stores; output statistics on the fly.
+#pragma once
+#include "rk_tc.cuh"
+
+namespace sfb {
+
+struct SkParams {
+  CUtensorMap tmA1;   // bf16 [K1, L, B]    box [64, 136 | 128, 1]
+  CUtensorMap tmA2;   // bf16 [K2, L, B2]   box [64, 128, 1]
+  CUtensorMap tmW;    // bf16 [K1 + K2, taps * N] box [64, BN]
+  CUtensorMap tmR;    // fp32 [N, L, B]     box [32, 128, 1]   residual in / fp32 out
+  CUtensorMap tmT;    // bf16 [N, L, B]     box [32, 128, 1], 64-byte swizzle   bf16 out
+  // A transform
+  int xf;                       // 0 none, 1 GroupNorm + SiLU, 2 LayerNorm (x Modulation when mod != null)
+  const double* stats_in;       // [B, 8, 2] group sums of A1 (xf == 1)
+  const float *gamma, *beta;    // [K1]
+  const float* rowstats_in;     // [B * L, rs_parts, 2] partial (sum, sum of squares) of every A1 / residual row
+  int rs_parts;
+  const float* mod;             // [2 * K1] Modulation scale | shift of this step, row (b % mod_bmod) * mod_bstride
+  int mod_bstride, mod_bmod;
+  // epilogue
+  const float* bias;            // [bias_mod] or null
+  const float* colscale;        // [bias_mod] or null, row (b % cs_bmod) * cs_bstride
+  const float* rowvec;          // [B, rowvec_stride] or null
+  int bias_mod, cs_bstride, cs_bmod, rowvec_stride;
+  int resid_mode;               // 0 none, 1 + resid, 2 + LayerNorm/Modulation(resid)
+  int has_out_r, has_out_t;
+  double* stats_out;            // [B, 8, 2] group sums of the output (group = (n / GS) % 8) or null
+  float* rowstats_out;          // [B * L, n_tiles, 2] or null
+  int L, tiles_per_clip, N, n_tiles, total_tiles, taps, k1_chunks, k2_chunks, K1, a2_bmod;
+  float eps;
+};
+
+template <int BN> struct SkCfg {
+  static constexpr int NA = BN == 256 ? 2 : 3;
+  static constexpr int NB = BN == 256 ? 3 : 5;
+  static constexpr int NR = 3;
+  static constexpr int A_BYTES = 136 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int R_BYTES = 128 * 128;    // [128 rows][32 fp32], 128B swizzle
+  static constexpr int T_BYTES = 128 * 64;     // [128 rows][32 bf16], 64B swizzle
+  static constexpr int KMAX = 1024;            // largest transformed K1
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + NA * A_BYTES;
+  static constexpr int OFF_R = OFF_B + NB * B_BYTES;
+  static constexpr int OFF_T = OFF_R + NR * R_BYTES;
+  static constexpr int OFF_TAB = OFF_T + NR * T_BYTES;         // [2][KMAX] per-channel transform coefficients
+  static constexpr int OFF_ROWTAB = OFF_TAB + 2 * KMAX * 4;    // [136][2] per-row mean, rstd
+  static constexpr int OFF_VEC = OFF_ROWTAB + 2 * 136 * 4 + 64;
+  static constexpr int OFF_BAR = OFF_VEC + 4 * BN * 4;
+  static constexpr int SMEM = OFF_BAR + 512;
+  static constexpr int kThreads = 384;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int BN, int GS>
+__global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkParams p) {
+  using C = SkCfg<BN>;
+  constexpr int NA = C::NA, NB = C::NB, NR = C::NR;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + C::OFF_A;
+  uint8_t* sB = smem + C::OFF_B;
+  uint8_t* sR = smem + C::OFF_R;
+  uint8_t* sT = smem + C::OFF_T;
+  float* tab_a = reinterpret_cast<float*>(smem + C::OFF_TAB);
+  float* tab_b = tab_a + C::KMAX;
+  float* rowtab = reinterpret_cast<float*>(smem + C::OFF_ROWTAB);
+  float* sVEC = reinterpret_cast<float*>(smem + C::OFF_VEC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* a_full = bars;                 // [NA]
+  uint64_t* a_empty = a_full + NA;         // [NA]
+  uint64_t* op_full = a_empty + NA;        // [NA]
+  uint64_t* b_full = op_full + NA;         // [NB]
+  uint64_t* b_empty = b_full + NB;         // [NB]
+  uint64_t* acc_full = b_empty + NB;       // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint64_t* rc_full = acc_empty + 2;       // [NR]
+  uint64_t* rc_empty = rc_full + NR;       // [NR]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rc_empty + NR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int pad = p.taps == 3 ? 1 : 0;
+  const int rows_a = p.taps == 3 ? 136 : 128;
+  constexpr int NCH = BN / 32;             // epilogue chunks per tile
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA1);
+    tma_prefetch_desc(&p.tmW);
+    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&op_full[s], 128); }
+    for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < NR; ++s) { mbar_init(&rc_full[s], 1); mbar_init(&rc_empty[s], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 3) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------- mainloop TMA producer
+      uint32_t ia = 0, ib = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n0 = (t % p.n_tiles) * BN;
+        const int mi = t / p.n_tiles;
+        const int b = mi / p.tiles_per_clip;
+        const int l0 = (mi % p.tiles_per_clip) * 128;
+        for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
+          const bool second = kc >= p.k1_chunks;
+          const int sa = ia % NA;
+          mbar_wait(&a_empty[sa], ((ia / NA) & 1) ^ 1);
+          if (!second) {
+            mbar_expect_tx(&a_full[sa], rows_a * 128);
+            tma_load_3d(sA + sa * C::A_BYTES, &p.tmA1, &a_full[sa], kc * 64, l0 - pad, b);
+          } else {
+            mbar_expect_tx(&a_full[sa], 128 * 128);
+            tma_load_3d(sA + sa * C::A_BYTES, &p.tmA2, &a_full[sa], (kc - p.k1_chunks) * 64, l0, b % p.a2_bmod);
+          }
+          const int ntap = second ? 1 : p.taps;
+          for (int tap = 0; tap < ntap; ++tap, ++ib) {
+            const int sb = ib % NB;
+            mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
+            mbar_expect_tx(&b_full[sb], C::B_BYTES);
+            tma_load_2d(sB + sb * C::B_BYTES, &p.tmW, &b_full[sb], second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64, tap * p.N + n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, BN, 0, 0);
+      uint32_t ia = 0, ib = 0, i = 0;
+      for (int t = t_begin; t < t_end; ++t, ++i) {
+        const uint32_t acc = i & 1;
+        mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * BN;
+        bool first = true;
+        for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
+          const bool second = kc >= p.k1_chunks;
+          const int sa = ia % NA;
+          mbar_wait(&a_full[sa], (ia / NA) & 1);
+          if (p.xf) mbar_wait(&op_full[sa], (ia / NA) & 1);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(sA + sa * C::A_BYTES);
+          const int ntap = second ? 1 : p.taps;
+          for (int tap = 0; tap < ntap; ++tap, ++ib) {
+            const int sb = ib % NB;
+            mbar_wait(&b_full[sb], (ib / NB) & 1);
+            tc_fence_after();
+            const uint32_t bbase = smem_u32(sB + sb * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_ss<false>(tacc, make_smem_desc_sw128(abase + tap * 128 + k * 32, 16, 1024),
+                             make_smem_desc_sw128(bbase + k * 32, 16, 1024), idesc, first ? 0u : 1u);
+              first = false;
+            }
+            umma_commit(&b_empty[sb]);
+          }
+          umma_commit(&a_empty[sa]);
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0 && p.resid_mode != 0) {
+      // ------------------------------------------------------------- epilogue TMA producer: residual chunks
+      uint32_t q = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n0 = (t % p.n_tiles) * BN;
+        const int mi = t / p.n_tiles;
+        const int b = mi / p.tiles_per_clip;
+        const int l0 = (mi % p.tiles_per_clip) * 128;
+        for (int c = 0; c < NCH; ++c, ++q) {
+          const int rs = q % NR;
+          mbar_wait(&rc_empty[rs], ((q / NR) & 1) ^ 1);
+          mbar_expect_tx(&rc_full[rs], C::R_BYTES);
+          tma_load_3d(sR + rs * C::R_BYTES, &p.tmR, &rc_full[rs], n0 + c * 32, l0, b);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    if (p.xf) {
+      // ------------------------------------------------------------- A transform (in place on the landed bf16 tile)
+      const int tid = threadIdx.x - 128;        // 0..127
+      const int g = tid & 7;                     // 16-byte chunk (8 channels) of the 128-byte row
+      const int rsub = tid >> 3;                 // 0..15
+      int cur_b = -1, cur_mi = -1;
+      uint32_t ia = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int mi = t / p.n_tiles;
+        const int b = mi / p.tiles_per_clip;
+        const int l0 = (mi % p.tiles_per_clip) * 128;
+        if (b != cur_b) {         // per-clip channel coefficients: y = x * a[c] + b[c]
+          cur_b = b;
+          named_bar(3, 128);
+          if (p.xf == 1) {
+            const int gsa = p.K1 / 8;
+            const double cnt = (double)p.L * gsa;
+            for (int c = tid; c < p.K1; c += 128) {
+              const int grp = c / gsa;
+              const double s1 = p.stats_in[(size_t)b * 16 + grp * 2], s2 = p.stats_in[(size_t)b * 16 + grp * 2 + 1];
+              const double mean = s1 / cnt;
+              double var = s2 / cnt - mean * mean;
+              var = var > 0.0 ? var : 0.0;
+              const float a = (float)(1.0 / sqrt(var + (double)p.eps)) * __ldg(&p.gamma[c]);
+              tab_a[c] = 0.5f * a;                                           // SiLU(y) = h tanh(h) + h, h = y / 2
+              tab_b[c] = 0.5f * (__ldg(&p.beta[c]) - (float)mean * a);
+            }
+          } else {
+            const float* md = p.mod ? p.mod + (size_t)(b % p.mod_bmod) * p.mod_bstride : nullptr;
+            for (int c = tid; c < p.K1; c += 128) {
+              tab_a[c] = md ? 1.f + md[c] : 1.f;
+              tab_b[c] = md ? md[p.K1 + c] : 0.f;
+            }
+          }
+          named_bar(3, 128);
+        }
+        if (p.xf == 2 && mi != cur_mi) {   // per-position LayerNorm statistics of this M tile's rows
+          cur_mi = mi;
+          named_bar(3, 128);
+          {
+            const int l = l0 + tid;
+            float mean = 0.f, rstd = 0.f;
+            if (l < p.L) {
+              const float* rsrc = p.rowstats_in + ((size_t)b * p.L + l) * p.rs_parts * 2;
+              float s1 = 0.f, s2 = 0.f;
+              for (int j = 0; j < p.rs_parts; ++j) { s1 += rsrc[2 * j]; s2 += rsrc[2 * j + 1]; }
+              mean = s1 / (float)p.K1;
+              rstd = rsqrtf(fmaxf(s2 / (float)p.K1 - mean * mean, 0.f) + p.eps);
+            }
+            rowtab[2 * tid] = mean;
+            rowtab[2 * tid + 1] = rstd;
+          }
+          named_bar(3, 128);
+        }
+        for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
+          const int sa = ia % NA;
+          mbar_wait(&a_full[sa], (ia / NA) & 1);
+          if (kc < p.k1_chunks) {
+            uint8_t* tile = sA + sa * C::A_BYTES;
+            float ca[8], cb[8];
+            {
+              const float4 a0 = *reinterpret_cast<const float4*>(&tab_a[kc * 64 + g * 8]), a1 = *reinterpret_cast<const float4*>(&tab_a[kc * 64 + g * 8 + 4]);
+              const float4 b0 = *reinterpret_cast<const float4*>(&tab_b[kc * 64 + g * 8]), b1 = *reinterpret_cast<const float4*>(&tab_b[kc * 64 + g * 8 + 4]);
+              ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+              cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
+            }
+#pragma unroll 3
+            for (int r = rsub; r < rows_a; r += 16) {
+              uint4* slot = reinterpret_cast<uint4*>(tile + r * 128 + ((g ^ (r & 7)) << 4));
+              const uint4 u = *slot;
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(w[j] << 16); v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+              const int l = l0 - pad + r;
+              uint4 o = make_uint4(0, 0, 0, 0);
+              if (l >= 0 && l < p.L) {
+                float y[8];
+                if (p.xf == 1) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float h = fmaf(v[j], ca[j], cb[j]);
+                    y[j] = fmaf(h, tanh_approx(h), h);
+                  }
+                } else {
+                  const float mean = rowtab[2 * r], rstd = rowtab[2 * r + 1];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[j] = fmaf((v[j] - mean) * rstd, ca[j], cb[j]);
+                }
+                o = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+              }
+              *slot = o;
+            }
+            fence_proxy_async();
+          }
+          mbar_arrive(&op_full[sa]);
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------- epilogue: one accumulator row per thread
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const int et = threadIdx.x - 256;          // 0..127
+    const bool elected = et == 0;
+    const uint32_t lane_off = uint32_t(q4 * 32) << 16;
+    const int sw = row & 7;
+    float* ep_mul = sVEC;             // [BN] colscale
+    float* ep_add = sVEC + BN;        // [BN] bias * colscale + rowvec
+    float* ep_g = sVEC + 2 * BN;      // [BN] 1 + modulation scale   (resid_mode 2)
+    float* ep_sh = sVEC + 3 * BN;     // [BN] modulation shift
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    int cur_b = -1, cur_n = -1, cur_goff = 0;
+    auto flush_stats = [&](int b, int goff) {
+      if (p.stats_out == nullptr || b < 0) return;
+      constexpr int NG = (BN / GS) < 8 ? (BN / GS) : 8;     // distinct local groups inside a tile (local index (c / GS) & 7)
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        float a = s1[k], c = s2[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+        if (lane == 0) {
+          const int grp = (k + goff) & 7;
+          atomicAdd(&p.stats_out[(size_t)b * 16 + grp * 2], (double)a);
+          atomicAdd(&p.stats_out[(size_t)b * 16 + grp * 2 + 1], (double)c);
+        }
+        s1[k] = 0.f; s2[k] = 0.f;
+      }
+    };
+    uint32_t i = 0, q = 0;
+    for (int t = t_begin; t < t_end; ++t, ++i) {
+      const int n_idx = t % p.n_tiles;
+      const int n0 = n_idx * BN;
+      const int mi = t / p.n_tiles;
+      const int b = mi / p.tiles_per_clip;
+      const int l0 = (mi % p.tiles_per_clip) * 128;
+      const bool row_valid = l0 + row < p.L;
+      const uint32_t acc = i & 1;
+      if (b != cur_b || n_idx != cur_n) {
+        const int goff = (n0 / GS) & 7;
+        if (b != cur_b || goff != cur_goff) flush_stats(cur_b, cur_goff);
+        cur_goff = goff;
+        named_bar(2, 128);
+        cur_b = b; cur_n = n_idx;
+        for (int n = et; n < BN; n += 128) {
+          const int nm = (n0 + n) % p.bias_mod;
+          const float cs = p.colscale ? p.colscale[(size_t)(b % p.cs_bmod) * p.cs_bstride + nm] : 1.f;
+          const float rv = p.rowvec ? p.rowvec[(size_t)b * p.rowvec_stride + nm] : 0.f;
+          ep_mul[n] = cs;
+          ep_add[n] = (p.bias ? p.bias[nm] : 0.f) * cs + rv;
+          if (p.resid_mode == 2) {
+            const float* md = p.mod + (size_t)(b % p.mod_bmod) * p.mod_bstride;
+            ep_g[n] = 1.f + md[n0 + n];
+            ep_sh[n] = md[p.N + n0 + n];
+          }
+        }
+        named_bar(2, 128);
+      }
+      float r_mean = 0.f, r_rstd = 0.f;
+      if (p.resid_mode == 2 && row_valid) {     // LayerNorm statistics of this thread's residual row
+        const float* rsrc = p.rowstats_in + ((size_t)b * p.L + l0 + row) * p.rs_parts * 2;
+        float a = 0.f, c = 0.f;
+        for (int j = 0; j < p.rs_parts; ++j) { a += rsrc[2 * j]; c += rsrc[2 * j + 1]; }
+        r_mean = a / (float)p.N;
+        r_rstd = rsqrtf(fmaxf(c / (float)p.N - r_mean * r_mean, 0.f) + p.eps);
+      }
+      mbar_wait(&acc_full[acc], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + acc * BN + lane_off;
+      float rsum = 0.f, rsq = 0.f;
+      // One 32-column chunk.  The chunk loop below is deliberately NOT unrolled beyond a pair: the unrolled epilogue of
+      // a 256-wide tile is ~64 KB of SASS, which misses the instruction cache on every tile (ncu: stall_no_inst).
+      auto process = [&](const int c, const uint32_t (&v)[32]) {
+        const int c0 = c * 32;
+        const int rs = q % NR;
+        uint8_t* rt = sR + rs * C::R_BYTES;
+        uint8_t* tt = sT + rs * C::T_BYTES;
+        if (p.resid_mode != 0) mbar_wait(&rc_full[rs], (q / NR) & 1);
+        float y[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 mu = *reinterpret_cast<const float4*>(&ep_mul[c0 + j4 * 4]);
+          const float4 ad = *reinterpret_cast<const float4*>(&ep_add[c0 + j4 * 4]);
+          uint8_t* slot = rt + row * 128 + ((j4 ^ sw) << 4);
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.resid_mode != 0) x = *reinterpret_cast<const float4*>(slot);
+          if (p.resid_mode == 2) {
+            const float4 gg = *reinterpret_cast<const float4*>(&ep_g[c0 + j4 * 4]);
+            const float4 sh = *reinterpret_cast<const float4*>(&ep_sh[c0 + j4 * 4]);
+            x.x = fmaf((x.x - r_mean) * r_rstd, gg.x, sh.x); x.y = fmaf((x.y - r_mean) * r_rstd, gg.y, sh.y);
+            x.z = fmaf((x.z - r_mean) * r_rstd, gg.z, sh.z); x.w = fmaf((x.w - r_mean) * r_rstd, gg.w, sh.w);
+          }
+          y[j4 * 4 + 0] = fmaf(__uint_as_float(v[j4 * 4 + 0]), mu.x, ad.x) + x.x;
+          y[j4 * 4 + 1] = fmaf(__uint_as_float(v[j4 * 4 + 1]), mu.y, ad.y) + x.y;
+          y[j4 * 4 + 2] = fmaf(__uint_as_float(v[j4 * 4 + 2]), mu.z, ad.z) + x.z;
+          y[j4 * 4 + 3] = fmaf(__uint_as_float(v[j4 * 4 + 3]), mu.w, ad.w) + x.w;
+          if (p.has_out_r) *reinterpret_cast<float4*>(slot) = make_float4(y[j4 * 4], y[j4 * 4 + 1], y[j4 * 4 + 2], y[j4 * 4 + 3]);
+        }
+        if (p.has_out_t) {      // [128 rows][64 B], 64-byte swizzle: 16-byte chunk j ^ ((row >> 1) & 3)
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8)
+            *reinterpret_cast<uint4*>(tt + row * 64 + ((j8 ^ ((row >> 1) & 3)) << 4)) =
+                make_uint4(pack_bf16(y[j8 * 8], y[j8 * 8 + 1]), pack_bf16(y[j8 * 8 + 2], y[j8 * 8 + 3]),
+                           pack_bf16(y[j8 * 8 + 4], y[j8 * 8 + 5]), pack_bf16(y[j8 * 8 + 6], y[j8 * 8 + 7]));
+        }
+        if (row_valid) {
+          if (p.stats_out != nullptr) {
+            constexpr int NSB = GS >= 32 ? 1 : 32 / GS;      // sub-blocks of one group inside the chunk
+            constexpr int SBW = 32 / NSB;
+            float ps1[NSB], ps2[NSB];
+#pragma unroll
+            for (int sb = 0; sb < NSB; ++sb) {
+              float a = 0.f, b2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < SBW; ++j) { a += y[sb * SBW + j]; b2 = fmaf(y[sb * SBW + j], y[sb * SBW + j], b2); }
+              ps1[sb] = a; ps2[sb] = b2;
+            }
+            if constexpr (NSB == 8) {      // GS = 4: the chunk holds all eight groups in order
+#pragma unroll
+              for (int k = 0; k < 8; ++k) { s1[k] += ps1[k]; s2[k] += ps2[k]; }
+            } else {                       // local group of sub-block sb = (c0 / GS + sb) & 7: predicated scatter
+              const int off = (c0 / GS) & 7;
+#pragma unroll
+              for (int sb = 0; sb < NSB; ++sb)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  if (((off + sb) & 7) == k) { s1[k] += ps1[sb]; s2[k] += ps2[sb]; }
+            }
+          }
+          if (p.rowstats_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { rsum += y[j]; rsq = fmaf(y[j], y[j], rsq); }
+          }
+        }
+        if (c == NCH - 1) {           // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[acc]);
+        }
+        fence_proxy_async();
+        named_bar(1, 128);
+        if (elected) {
+          if (p.has_out_r) tma_store_3d(&p.tmR, rt, n0 + c0, l0, b);
+          if (p.has_out_t) tma_store_3d(&p.tmT, tt, n0 + c0, l0, b);
+          bulk_commit();
+          bulk_wait_read<1>();                               // the previous chunk's stores no longer read their buffers
+          if (p.resid_mode != 0 && q > 0) mbar_arrive(&rc_empty[(q - 1) % NR]);
+        }
+        ++q;
+      };
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tacc, v0);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        tmem_ld_wait();
+        tmem_ld32(tacc + (c + 1) * 32, v1);
+        process(c, v0);
+        tmem_ld_wait();
+        if (c + 2 < NCH) tmem_ld32(tacc + (c + 2) * 32, v0);
+        process(c + 1, v1);
+      }
+      if (p.rowstats_out != nullptr && row_valid) {
+        float* dst = p.rowstats_out + (((size_t)b * p.L + l0 + row) * p.n_tiles + n_idx) * 2;
+        dst[0] = rsum;
+        dst[1] = rsq;
+      }
+    }
+    flush_stats(cur_b, cur_goff);
+    if (elected) bulk_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------------ instantiation table
+#define SFB_SK_LIST(X) X(128, 4) X(128, 8) X(128, 16) X(256, 8) X(256, 16) X(256, 32) X(256, 64) X(256, 128)
+
+inline int sk_find(int BN, int GS) {
+  int i = 0;
+#define X(a, b) if (BN == a && GS == b) return i; ++i;
+  SFB_SK_LIST(X)
+#undef X
+  return -1;
+}
+inline cudaError_t sk_set_attrs() {
+  cudaError_t e = cudaSuccess;
+#define X(a, b) if (e == cudaSuccess) e = cudaFuncSetAttribute(sk_kernel<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<a>::SMEM);
+  SFB_SK_LIST(X)
+#undef X
+  return e;
+}
+inline void sk_launch(int id, const SkParams& p, int num_sms, cudaStream_t st) {
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  int i = 0;
+#define X(a, b) if (id == i++) { sk_kernel<a, b><<<grid, 384, SkCfg<a>::SMEM, st>>>(p); return; }
+  SFB_SK_LIST(X)
+#undef X
+}
+
+}  // namespace sfb
