@@ -13,8 +13,8 @@ finished waveforms is inside the timed region.
 
 Rank 0 prints ONE JSON line.  `value` = whole-job clips/s with inputs resident in HBM; `e2e` = the same through the
 public API with pinned HOST inputs (H2D + D2H inside the timed region); `roofline` = the dominant kernel
-(gemm_tc_kernel: tcgen05 implicit-GEMM) - algorithmic FLOPs of its launches / their CUDA-event durations, measured
-live on a profiled replica of the step; `cpu_baseline` = the oracle on this box's host cores on a bounded sample.
+(sk_kernel: streaming-K fused tcgen05 implicit GEMM) - algorithmic FLOPs of its launches / their CUDA-event durations,
+measured live on a profiled replica of the step; `cpu_baseline` = the oracle on this box's host cores on a bounded sample.
 """
 from __future__ import annotations
 
@@ -255,18 +255,33 @@ def main():
         a = by.setdefault(k, dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
         a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["n"] += 1
     eval_ms = sum(a["ms"] for a in by.values())
-    g = by.get("gemm", dict(ms=1e-9, flops=0, n=1))
+    # dominant kernel: the streaming-K fused tcgen05 GEMM (sk_kernel; fp32 mode: gemm_tc_kernel) - every conv / inject /
+    # projection / down / up of depths 3-7, i.e. ~95 % of the algorithmic FLOPs
+    dom = "sk" if "sk" in by else "gemm"
+    g = by.get(dom, dict(ms=1e-9, flops=0, n=1))
     ach = g["flops"] / (g["ms"] / 1e3) / 1e12
     peak = peaks["bf16_sustained"] if args.precision == "bf16" else peaks["bf16_sustained"] / 2
-    roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit-GEMM: conv3 / inject / qkv / out / down / up)", "bound": "tensor",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_sk_traffic.json")       # dram bytes of the same launches from `ncu --set full`
+    if os.path.exists(tpath) and args.precision == "bf16" and B == 16 and L == 262144:
+        try:
+            traffic = json.load(open(tpath))["dram_bytes_per_launch_avg"]
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "sk_kernel (streaming-K fused tcgen05 implicit GEMM: GN/LN prologue, conv3 / inject / qkv / out / down / up)"
+                          if dom == "sk" else "gemm_tc_kernel (tcgen05 implicit GEMM)", "bound": "tensor",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "launches_per_eval": g["n"], "share_of_eval_time": g["ms"] / eval_ms,
+                "algorithmic_flops_per_launch_avg": g["flops"] / max(g["n"], 1), "launches_per_eval": g["n"],
+                "avg_launch_ms": g["ms"] / max(g["n"], 1), "share_of_eval_time": g["ms"] / eval_ms,
                 "per_kernel": {k: {"ms_per_eval": round(a["ms"], 4), "launches": a["n"],
                                    "tflops": round(a["flops"] / (a["ms"] / 1e3) / 1e12, 2) if a["ms"] > 0 else None,
                                    "gbs": round(a["bytes"] / (a["ms"] / 1e3) / 1e9, 1) if a["ms"] > 0 else None,
                                    "share": round(a["ms"] / eval_ms, 4)} for k, a in sorted(by.items())},
-                "hbm_peak_gbs": peaks["hbm"]}
+                "hbm_peak_gbs": peaks["hbm"],
+                "hbm_bound_kernel": {"kernel": "rk_kernel (resident-weight fused items, depths 1-2)",
+                                     "achieved_gbs": (by["rk"]["bytes"] / (by["rk"]["ms"] / 1e3) / 1e9) if "rk" in by else None,
+                                     "frac_of_measured_hbm": (by["rk"]["bytes"] / (by["rk"]["ms"] / 1e3) / 1e9 / peaks["hbm"]) if "rk" in by else None}}
     evals = 2 if args.scale != 1.0 else 1
     f_eval = F_EVAL_GFLOP[args.upsample_mode] * (L / 262144.0) * 1e9
     roofline["end_to_end_frac_of_bf16_peak"] = value / world * NS * evals * f_eval / (peaks["bf16_sustained"] * 1e12)

@@ -107,6 +107,9 @@ int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len);
  * "index kind depth stack item ms flops bytes" (algorithmic flops / bytes).  bench.py's roofline comes from this. */
 int sfb_dbg_profile(sfb_handle* h, int enable);
 int sfb_dbg_profile_report(sfb_handle* h, char* buf, int buf_len);
+/* Device-clock timeline of one streaming-K plan op (CTA 0): attach with op_index >= 0, run an evaluation, then read
+ * back with host_buf != NULL (8 roles x 256 clock64 stamps; tools/sk_timeline.py decodes them). */
+int sfb_dbg_sk_timeline(sfb_handle* h, int op_index, long long* host_buf, int n);
 /* Stand-alone kernels on raw device buffers (unit tests):
  *   gemm: out = resid + (A1 (*) W + A2 W2 + bias), A* [B, L, K*] in operand precision (bf16 or f32 per `bf16`),
  *         W [taps*N, K1+K2] same precision, out_r f32 / out_t operand precision (nullable), stats f64 [B,8,2]. */

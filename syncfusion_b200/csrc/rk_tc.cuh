@@ -59,6 +59,55 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ uint32_t pack_bf16_rn(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// SiLU of two values on the FMA pipe + HALF a MUFU op each.  MUFU is the scarce unit here (measured on B200: a
+// [136 x 64] tile of tanh.approx / ex2+rcp costs 2200-3200 cycles per SM, more than the tile's 1536 MMA cycles):
+//   silu(z) = z / (1 + 2^(-z log2 e));  2^t for two elements with ONE packed ex2.approx.ftz.bf16x2 (sigma = 1 / (1 + e) is
+//   well conditioned in e, so the bf16 precision of e costs <= 2^-9 relative, the precision of the bf16 result), and the
+//   reciprocal by a bit-trick seed + two Newton steps (relative error ~2e-4) instead of MUFU.RCP.
+__device__ __forceinline__ void silu2(float z0, float z1, float& y0, float& y1) {
+  const float t0 = fminf(z0 * -1.4426950408889634f, 64.f), t1 = fminf(z1 * -1.4426950408889634f, 64.f);
+  uint32_t pk, e;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(t1), "f"(t0));
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(e) : "r"(pk));
+  const float d0 = 1.f + __uint_as_float(e << 16), d1 = 1.f + __uint_as_float(e & 0xFFFF0000u);
+  float r0 = __uint_as_float(0x7EF311C7u - __float_as_uint(d0)), r1 = __uint_as_float(0x7EF311C7u - __float_as_uint(d1));
+  r0 = r0 * fmaf(-d0, r0, 2.f); r1 = r1 * fmaf(-d1, r1, 2.f);
+  r0 = r0 * fmaf(-d0, r0, 2.f); r1 = r1 * fmaf(-d1, r1, 2.f);
+  y0 = z0 * r0; y1 = z1 * r1;
+}
+// Packed bf16x2 SiLU(GroupNorm(x)) for UMMA operand tiles: h = x * a' + b' (a' = a / 2, b' = b / 2 split hi + lo so the
+// per-channel offset keeps fp32-like precision), y = h * tanh(h) + h.  Three FMA-pipe ops and one MUFU op per PAIR of
+// elements, no unpack / pack: the transform warps are instruction-issue bound (measured: ~4 cycles per instruction per
+// warp), and the fp32 form costs ~11 instructions per element against ~2 here.
+__device__ __forceinline__ uint32_t silu_gn_bf16x2(uint32_t x, uint32_t pa, uint32_t pbh, uint32_t pbl) {
+  uint32_t h, t, y;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(x), "r"(pa), "r"(pbh));
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(h) : "r"(h), "r"(pbl));
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(h));
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(y) : "r"(h), "r"(t), "r"(h));
+  return y;
+}
+// (a, b) fp32 -> packed halves for channel pair (c, c + 1): a' = a / 2, b' = b / 2 = hi + lo
+__device__ __forceinline__ void gn_pack_coef(float a0, float b0, float a1, float b1, uint32_t& pa, uint32_t& pbh, uint32_t& pbl) {
+  pa = pack_bf16_rn(0.5f * a0, 0.5f * a1);
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(0.5f * b0), h1 = __float2bfloat16_rn(0.5f * b1);
+  pbh = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  pbl = pack_bf16_rn(0.5f * b0 - __bfloat162float(h0), 0.5f * b1 - __bfloat162float(h1));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -250,6 +299,7 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
     const int g = tid % G, rsub = tid / G;
     constexpr int GSA = K1 / 8;                  // GroupNorm group size of the A tensor (8 groups)
     float ca[8], cb[8];
+    uint32_t pa[4], pbh[4], pbl[4];
     int cur_b = -1;
     uint32_t i = 0;
     for (int t = t_begin; t < t_end; ++t, ++i) {
@@ -258,54 +308,75 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
       const int s = i & 1;
       if (b != cur_b) {
         cur_b = b;
-        const double cnt = (double)p.L * GSA;
+        const double inv_cnt = 1.0 / ((double)p.L * GSA);   // fp64 only where E[x^2] - mean^2 cancels; no fp64 div / sqrt per channel
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int ch = g * 8 + j, grp = ch / GSA;
           const double s1 = p.stats_in[(size_t)b * 16 + grp * 2], s2 = p.stats_in[(size_t)b * 16 + grp * 2 + 1];
-          const double mean = s1 / cnt;
-          double var = s2 / cnt - mean * mean;
-          var = var > 0.0 ? var : 0.0;
-          const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-          const float a = rstd * __ldg(&p.gamma[ch]);
-          // SiLU(y) = h * tanh(h) + h with h = y / 2: one MUFU per element
-          ca[j] = 0.5f * a;
-          cb[j] = 0.5f * (__ldg(&p.beta[ch]) - (float)mean * a);
+          const double mean = s1 * inv_cnt;
+          const double var = fma(-mean, mean, s2 * inv_cnt);
+          const float a = rsqrtf(fmaxf((float)var, 0.f) + p.eps) * __ldg(&p.gamma[ch]);
+          ca[j] = a;
+          cb[j] = __ldg(&p.beta[ch]) - (float)mean * a;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gn_pack_coef(ca[2 * j], cb[2 * j], ca[2 * j + 1], cb[2 * j + 1], pa[j], pbh[j], pbl[j]);
       }
       mbar_wait(&a_full[s], (i >> 1) & 1);
       uint8_t* op = sOP + s * C::OP_BYTES + (g / 8) * C::ATOM_A;
       const int co = g % 8;
-#pragma unroll 2
-      for (int r0 = 0; r0 < C::ROWS_A; r0 += RPI) {
-        const int r = r0 + rsub;
+      constexpr int NIT = (C::ROWS_A + RPI - 1) / RPI;
+      // load every row first, then compute, then store: independent chains overlap the LDS / MUFU latencies
+      uint4 u0[NIT], u1[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int r = it * RPI + rsub;
         if (r < C::ROWS_A) {
-          const int l = l0 - (TAPS == 3 ? 1 : 0) + r;
-          float v[8];
           if (XF == 2) {
             const uint8_t* raw = sRAW + s * C::RAW_BYTES + (g / 4) * C::ATOM_A + r * 128;
             const int c0 = (g % 4) * 2;
-            const float4 x0 = *reinterpret_cast<const float4*>(raw + ((c0 ^ (r & 7)) << 4));
-            const float4 x1 = *reinterpret_cast<const float4*>(raw + (((c0 + 1) ^ (r & 7)) << 4));
-            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+            u0[it] = *reinterpret_cast<const uint4*>(raw + ((c0 ^ (r & 7)) << 4));
+            u1[it] = *reinterpret_cast<const uint4*>(raw + (((c0 + 1) ^ (r & 7)) << 4));
           } else {
-            const uint4 u = *reinterpret_cast<const uint4*>(op + r * 128 + ((co ^ (r & 7)) << 4));
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(w[j] << 16); v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+            u0[it] = *reinterpret_cast<const uint4*>(op + r * 128 + ((co ^ (r & 7)) << 4));
           }
-          uint4 o = make_uint4(0, 0, 0, 0);
-          if (l >= 0 && l < p.L) {   // conv zero padding applies AFTER the activation: out-of-clip rows stay zero
-            float y[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float h = fmaf(v[j], ca[j], cb[j]);
-              y[j] = fmaf(h, tanh_approx(h), h);
-            }
-            o = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
-          }
-          *reinterpret_cast<uint4*>(op + r * 128 + ((co ^ (r & 7)) << 4)) = o;
         }
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int r = it * RPI + rsub;
+        const int l = l0 - (TAPS == 3 ? 1 : 0) + r;
+        const bool ok = l >= 0 && l < p.L;       // conv zero padding applies AFTER the activation: out-of-clip rows stay zero
+        if (XF == 1) {      // bf16 raw tile: packed bf16x2 path, in place
+          const uint32_t w[4] = {u0[it].x, u0[it].y, u0[it].z, u0[it].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = ok ? silu_gn_bf16x2(w[j], pa[j], pbh[j], pbl[j]) : 0u;
+          u0[it] = make_uint4(o[0], o[1], o[2], o[3]);
+          continue;
+        }
+        float v[8];
+        if (XF == 2) {
+          v[0] = __uint_as_float(u0[it].x); v[1] = __uint_as_float(u0[it].y); v[2] = __uint_as_float(u0[it].z); v[3] = __uint_as_float(u0[it].w);
+          v[4] = __uint_as_float(u1[it].x); v[5] = __uint_as_float(u1[it].y); v[6] = __uint_as_float(u1[it].z); v[7] = __uint_as_float(u1[it].w);
+        } else {
+          const uint32_t w[4] = {u0[it].x, u0[it].y, u0[it].z, u0[it].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(w[j] << 16); v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+        }
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          silu2(fmaf(v[j], ca[j], cb[j]), fmaf(v[j + 1], ca[j + 1], cb[j + 1]), y[j], y[j + 1]);
+          y[j] = ok ? y[j] : 0.f;
+          y[j + 1] = ok ? y[j + 1] : 0.f;
+        }
+        u0[it] = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int r = it * RPI + rsub;
+        if (r < C::ROWS_A) *reinterpret_cast<uint4*>(op + r * 128 + ((co ^ (r & 7)) << 4)) = u0[it];
       }
       fence_proxy_async();
       mbar_arrive(&op_full[s]);

@@ -153,6 +153,7 @@ struct EngineBase {
   virtual int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes) = 0;
   virtual int op_info(int i, char* buf, int len) = 0;
   virtual int profile_report(char* buf, int len) = 0;
+  virtual int sk_timeline(int op_index, long long* host_buf, int n) { (void)op_index; (void)host_buf; (void)n; return SFB_ERR_UNSUPPORTED; }
   bool profiling = false;
   int fail(int code, const char* fmt, ...) {
     char b[512];
@@ -727,7 +728,7 @@ struct Engine : EngineBase {
     if (g.K2 > 0) { if (!make_tmap3<__nv_bfloat16>(&p.tmA2, a2, g.K2, L, B2, 64, 128)) return false; }
     else p.tmA2 = p.tmA1;
     if (!make_tmap2<__nv_bfloat16>(&p.tmW, g.w, (uint64_t)(g.K1 + g.K2), (uint64_t)g.taps * g.N, 64, BN)) return false;
-    p.tmR = p.tmA1; p.tmT = p.tmA1;
+    p.tmR = p.tmA1; p.tmRs = p.tmA1; p.tmT = p.tmA1;
     p.L = L; p.tiles_per_clip = (L + 127) / 128; p.N = g.N; p.n_tiles = g.N / BN;
     p.total_tiles = Beff * p.tiles_per_clip * p.n_tiles;
     p.taps = g.taps; p.k1_chunks = g.K1 / 64; p.k2_chunks = (g.K2 + 63) / 64; p.K1 = g.K1; p.a2_bmod = B2 > 0 ? B2 : 1;
@@ -742,12 +743,13 @@ struct Engine : EngineBase {
     op.out_r = ptr; op.sp.has_out_r = 1; op.sp.resid_mode = resid_mode;
     if (resid_mode) op.resid = ptr;
     op.bytes += (double)op.B * op.L * op.sp.N * (resid_mode ? 8 : 4);
-    return make_tmap3<float>(&op.sp.tmR, ptr, op.sp.N, op.L, op.B, 32, 128);
+    return make_tmap3<float>(&op.sp.tmR, ptr, op.sp.N, op.L, op.B, 16, 128, CU_TENSOR_MAP_SWIZZLE_64B) &&
+           make_tmap3<float>(&op.sp.tmRs, ptr, op.sp.N, op.L, op.B, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   }
   bool sk_out_t(Op& op, void* ptr) {
     op.out_t = ptr; op.sp.has_out_t = 1;
     op.bytes += (double)op.B * op.L * op.sp.N * 2;
-    return make_tmap3<__nv_bfloat16>(&op.sp.tmT, ptr, op.sp.N, op.L, op.B, 32, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+    return make_tmap3<__nv_bfloat16>(&op.sp.tmT, ptr, op.sp.N, op.L, op.B, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
   }
   void set_dbg(Op& op, int rows, int cols) {
     if (op.out_r) { op.dbg_off = (uint8_t*)op.out_r - wsb; op.dbg_dtype = 0; op.dbg_bytes = (size_t)rows * cols * 4; }
@@ -797,7 +799,7 @@ struct Engine : EngineBase {
       Op o = base("conv2"); o.in = P1; o.stats_in = sB;
       if (!add_sk(o, I.conv2, P1, L, Beff, nullptr, 0, 0) || !sk_out_r(o, A, 1) || !sk_out_t(o, P0)) return fail(SFB_ERR_CUDA, err_fmt, "conv2", d);
       o.sp.xf = 1; o.sp.stats_in = sB; o.sp.gamma = I.gn2_g; o.sp.beta = I.gn2_b; o.sp.rowstats_out = RS1;
-      parts1 = o.sp.n_tiles;
+      parts1 = 2 * o.sp.n_tiles;
       set_dbg(o, rows, C); plan.ops.push_back(o);
     }
     const bool last_is_inject = !I.has_attn;
@@ -813,7 +815,7 @@ struct Engine : EngineBase {
       } else {
         o.sp.rowstats_out = RS2;
       }
-      parts2 = o.sp.n_tiles;
+      parts2 = 2 * o.sp.n_tiles;
       set_dbg(o, rows, C); plan.ops.push_back(o);
     }
     xt_cur[d] = P1;
@@ -1068,6 +1070,22 @@ struct Engine : EngineBase {
     return SFB_OK;
   }
   double* inner_out_stats = nullptr;
+  long long* tl_buf = nullptr;   // sk timeline (debug): 8 roles x 256 stamps
+  // op_index >= 0: attach the timeline buffer to that plan op (must be an sk op) ; host_buf != null: read it back
+  int sk_timeline(int op_index, long long* host_buf, int n) override {
+    if (!tl_buf) { if (cudaMalloc(&tl_buf, 8 * 256 * 8) != cudaSuccess) return fail(SFB_ERR_CUDA, "timeline alloc"); owned.push_back(tl_buf); }
+    if (host_buf) {
+      SFB_CUDA(cudaDeviceSynchronize());
+      SFB_CUDA(cudaMemcpy(host_buf, tl_buf, sizeof(long long) * std::min(n, 8 * 256), cudaMemcpyDeviceToHost));
+    }
+    for (Op& o : plan.ops) o.sp.dbg = nullptr;
+    if (op_index >= 0) {
+      if (op_index >= (int)plan.ops.size() || plan.ops[op_index].kind != OP_SK) return fail(SFB_ERR_INVALID, "op %d is not an sk op", op_index);
+      SFB_CUDA(cudaMemset(tl_buf, 0, 8 * 256 * 8));
+      plan.ops[op_index].sp.dbg = tl_buf;
+    }
+    return SFB_OK;
+  }
   std::vector<cudaEvent_t> prof_ev;   // 2 per op: events around every launch of the most recent U-Net evaluation
 
   // One line per plan op: "index kind depth stack item ms flops bytes" (algorithmic flops / bytes of the op).
@@ -1499,6 +1517,10 @@ int sfb_dbg_profile(sfb_handle* h, int enable) {
 int sfb_dbg_profile_report(sfb_handle* h, char* buf, int buf_len) {
   if (!h || !buf) return SFB_ERR_INVALID;
   return h->e->profile_report(buf, buf_len);
+}
+int sfb_dbg_sk_timeline(sfb_handle* h, int op_index, long long* host_buf, int n) {
+  if (!h) return SFB_ERR_INVALID;
+  return h->e->sk_timeline(op_index, host_buf, n);
 }
 int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len) {
   if (!h || !buf) return SFB_ERR_INVALID;

@@ -25,8 +25,9 @@ struct SkParams {
   CUtensorMap tmA1;   // bf16 [K1, L, B]    box [64, 136 | 128, 1]
   CUtensorMap tmA2;   // bf16 [K2, L, B2]   box [64, 128, 1]
   CUtensorMap tmW;    // bf16 [K1 + K2, taps * N] box [64, BN]
-  CUtensorMap tmR;    // fp32 [N, L, B]     box [32, 128, 1]   residual in / fp32 out
-  CUtensorMap tmT;    // bf16 [N, L, B]     box [32, 128, 1], 64-byte swizzle   bf16 out
+  CUtensorMap tmR;    // fp32 [N, L, B]     box [16, 128, 1], 64-byte swizzle   residual in (two loads per 32-column chunk)
+  CUtensorMap tmRs;   // fp32 [N, L, B]     box [16, 32, 1],  64-byte swizzle   fp32 out (one store per epilogue warp)
+  CUtensorMap tmT;    // bf16 [N, L, B]     box [16, 32, 1],  no swizzle        bf16 out (one store per epilogue warp)
   // A transform
   int xf;                       // 0 none, 1 GroupNorm + SiLU, 2 LayerNorm (x Modulation when mod != null)
   const double* stats_in;       // [B, 8, 2] group sums of A1 (xf == 1)
@@ -46,34 +47,38 @@ struct SkParams {
   float* rowstats_out;          // [B * L, n_tiles, 2] or null
   int L, tiles_per_clip, N, n_tiles, total_tiles, taps, k1_chunks, k2_chunks, K1, a2_bmod;
   float eps;
+  long long* dbg;               // optional timeline buffer (CTA 0 only): [role][256] clock64 stamps (tools/sk_timeline.py)
 };
+
+#define SK_STAMP(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
 
 template <int BN> struct SkCfg {
   static constexpr int NA = BN == 256 ? 2 : 3;
   static constexpr int NB = BN == 256 ? 3 : 5;
-  static constexpr int NR = 3;
+  static constexpr int NR = 4;                 // residual / fp32-out chunk ring (in place)
+  static constexpr int NT = 2;                 // bf16-out chunk ring
   static constexpr int A_BYTES = 136 * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int R_BYTES = 128 * 128;    // [128 rows][32 fp32], 128B swizzle
-  static constexpr int T_BYTES = 128 * 64;     // [128 rows][32 bf16], 64B swizzle
+  static constexpr int R_BYTES = 128 * 128;    // [2 column halves][128 rows][16 fp32], 64B swizzle
+  static constexpr int T_BYTES = 128 * 64;     // [2 column halves][4 lane quarters][32 rows][16 bf16], dense
   static constexpr int KMAX = 1024;            // largest transformed K1
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + NA * A_BYTES;
   static constexpr int OFF_R = OFF_B + NB * B_BYTES;
   static constexpr int OFF_T = OFF_R + NR * R_BYTES;
-  static constexpr int OFF_TAB = OFF_T + NR * T_BYTES;         // [2][KMAX] per-channel transform coefficients
+  static constexpr int OFF_TAB = OFF_T + NT * T_BYTES;         // [2][KMAX] per-channel transform coefficients
   static constexpr int OFF_ROWTAB = OFF_TAB + 2 * KMAX * 4;    // [136][2] per-row mean, rstd
   static constexpr int OFF_VEC = OFF_ROWTAB + 2 * 136 * 4 + 64;
   static constexpr int OFF_BAR = OFF_VEC + 4 * BN * 4;
   static constexpr int SMEM = OFF_BAR + 512;
-  static constexpr int kThreads = 384;
+  static constexpr int kThreads = 512;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
 template <int BN, int GS>
-__global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkParams p) {
+__global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkParams p) {
   using C = SkCfg<BN>;
-  constexpr int NA = C::NA, NB = C::NB, NR = C::NR;
+  constexpr int NA = C::NA, NB = C::NB, NR = C::NR, NT = C::NT;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + C::OFF_A;
   uint8_t* sB = smem + C::OFF_B;
@@ -107,8 +112,8 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
     tma_prefetch_desc(&p.tmW);
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&op_full[s], 128); }
     for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
-    for (int s = 0; s < NR; ++s) { mbar_init(&rc_full[s], 1); mbar_init(&rc_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
+    for (int s = 0; s < NR; ++s) { mbar_init(&rc_full[s], 1); mbar_init(&rc_empty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 3) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SK_STAMP(7, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -137,12 +143,14 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
             mbar_expect_tx(&a_full[sa], 128 * 128);
             tma_load_3d(sA + sa * C::A_BYTES, &p.tmA2, &a_full[sa], (kc - p.k1_chunks) * 64, l0, b % p.a2_bmod);
           }
+          SK_STAMP(0, ia);
           const int ntap = second ? 1 : p.taps;
           for (int tap = 0; tap < ntap; ++tap, ++ib) {
             const int sb = ib % NB;
             mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
             mbar_expect_tx(&b_full[sb], C::B_BYTES);
             tma_load_2d(sB + sb * C::B_BYTES, &p.tmW, &b_full[sb], second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64, tap * p.N + n0);
+            SK_STAMP(1, ib);
           }
         }
       }
@@ -165,6 +173,7 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
           if (p.xf) mbar_wait(&op_full[sa], (ia / NA) & 1);
           tc_fence_after();
           const uint32_t abase = smem_u32(sA + sa * C::A_BYTES);
+          SK_STAMP(3, ia);
           const int ntap = second ? 1 : p.taps;
           for (int tap = 0; tap < ntap; ++tap, ++ib) {
             const int sb = ib % NB;
@@ -198,6 +207,7 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
           mbar_wait(&rc_empty[rs], ((q / NR) & 1) ^ 1);
           mbar_expect_tx(&rc_full[rs], C::R_BYTES);
           tma_load_3d(sR + rs * C::R_BYTES, &p.tmR, &rc_full[rs], n0 + c * 32, l0, b);
+          tma_load_3d(sR + rs * C::R_BYTES + C::R_BYTES / 2, &p.tmR, &rc_full[rs], n0 + c * 32 + 16, l0, b);
         }
       }
     }
@@ -218,16 +228,25 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
           named_bar(3, 128);
           if (p.xf == 1) {
             const int gsa = p.K1 / 8;
-            const double cnt = (double)p.L * gsa;
+            const double inv_cnt = 1.0 / ((double)p.L * gsa);      // one fp64 division per thread; no fp64 div / sqrt per channel
             for (int c = tid; c < p.K1; c += 128) {
               const int grp = c / gsa;
               const double s1 = p.stats_in[(size_t)b * 16 + grp * 2], s2 = p.stats_in[(size_t)b * 16 + grp * 2 + 1];
-              const double mean = s1 / cnt;
-              double var = s2 / cnt - mean * mean;
-              var = var > 0.0 ? var : 0.0;
-              const float a = (float)(1.0 / sqrt(var + (double)p.eps)) * __ldg(&p.gamma[c]);
-              tab_a[c] = 0.5f * a;                                           // SiLU(y) = h tanh(h) + h, h = y / 2
-              tab_b[c] = 0.5f * (__ldg(&p.beta[c]) - (float)mean * a);
+              const double mean = s1 * inv_cnt;
+              const double var = fma(-mean, mean, s2 * inv_cnt);
+              const float a = rsqrtf(fmaxf((float)var, 0.f) + p.eps) * __ldg(&p.gamma[c]);
+              tab_a[c] = a;
+              tab_b[c] = __ldg(&p.beta[c]) - (float)mean * a;
+            }
+            named_bar(3, 128);
+            // packed bf16x2 coefficient tables (pair c2 = channels 2 c2, 2 c2 + 1) overwrite the fp32 ones afterwards
+            uint32_t pk[3][C::KMAX / 2 / 128];
+            for (int c2 = tid, k = 0; c2 < p.K1 / 2; c2 += 128, ++k)
+              gn_pack_coef(tab_a[2 * c2], tab_b[2 * c2], tab_a[2 * c2 + 1], tab_b[2 * c2 + 1], pk[0][k], pk[1][k], pk[2][k]);
+            named_bar(3, 128);
+            uint32_t* tabp = reinterpret_cast<uint32_t*>(tab_a);
+            for (int c2 = tid, k = 0; c2 < p.K1 / 2; c2 += 128, ++k) {
+              tabp[c2] = pk[0][k]; tabp[C::KMAX / 2 + c2] = pk[1][k]; tabp[C::KMAX + c2] = pk[2][k];
             }
           } else {
             const float* md = p.mod ? p.mod + (size_t)(b % p.mod_bmod) * p.mod_bstride : nullptr;
@@ -259,56 +278,80 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
         for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
           const int sa = ia % NA;
           mbar_wait(&a_full[sa], (ia / NA) & 1);
+          if (tid == 0) SK_STAMP(2, 2 * ia);
           if (kc < p.k1_chunks) {
             uint8_t* tile = sA + sa * C::A_BYTES;
             float ca[8], cb[8];
-            {
+            uint32_t pa[4], pbh[4], pbl[4];
+            if (p.xf == 1) {
+              const uint32_t* tabp = reinterpret_cast<const uint32_t*>(tab_a);
+              const uint4 q0 = *reinterpret_cast<const uint4*>(&tabp[kc * 32 + g * 4]);
+              const uint4 q1 = *reinterpret_cast<const uint4*>(&tabp[C::KMAX / 2 + kc * 32 + g * 4]);
+              const uint4 q2 = *reinterpret_cast<const uint4*>(&tabp[C::KMAX + kc * 32 + g * 4]);
+              pa[0] = q0.x; pa[1] = q0.y; pa[2] = q0.z; pa[3] = q0.w;
+              pbh[0] = q1.x; pbh[1] = q1.y; pbh[2] = q1.z; pbh[3] = q1.w;
+              pbl[0] = q2.x; pbl[1] = q2.y; pbl[2] = q2.z; pbl[3] = q2.w;
+            } else {
               const float4 a0 = *reinterpret_cast<const float4*>(&tab_a[kc * 64 + g * 8]), a1 = *reinterpret_cast<const float4*>(&tab_a[kc * 64 + g * 8 + 4]);
               const float4 b0 = *reinterpret_cast<const float4*>(&tab_b[kc * 64 + g * 8]), b1 = *reinterpret_cast<const float4*>(&tab_b[kc * 64 + g * 8 + 4]);
               ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
               cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
             }
-#pragma unroll 3
-            for (int r = rsub; r < rows_a; r += 16) {
-              uint4* slot = reinterpret_cast<uint4*>(tile + r * 128 + ((g ^ (r & 7)) << 4));
-              const uint4 u = *slot;
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-              float v[8];
+            uint4 u[9];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { v[2 * j] = __uint_as_float(w[j] << 16); v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+            for (int it = 0; it < 9; ++it) {
+              const int r = rsub + 16 * it;
+              if (r < rows_a) u[it] = *reinterpret_cast<const uint4*>(tile + r * 128 + ((g ^ (r & 7)) << 4));
+            }
+#pragma unroll
+            for (int it = 0; it < 9; ++it) {
+              const int r = rsub + 16 * it;
               const int l = l0 - pad + r;
-              uint4 o = make_uint4(0, 0, 0, 0);
-              if (l >= 0 && l < p.L) {
-                float y[8];
-                if (p.xf == 1) {
+              const bool ok = l >= 0 && l < p.L;      // conv zero padding applies AFTER the activation
+              const uint32_t w[4] = {u[it].x, u[it].y, u[it].z, u[it].w};
+              if (p.xf == 1) {      // GroupNorm apply + SiLU, packed bf16x2 (see silu_gn_bf16x2)
+                uint32_t o[4];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float h = fmaf(v[j], ca[j], cb[j]);
-                    y[j] = fmaf(h, tanh_approx(h), h);
-                  }
-                } else {
-                  const float mean = rowtab[2 * r], rstd = rowtab[2 * r + 1];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] = fmaf((v[j] - mean) * rstd, ca[j], cb[j]);
-                }
-                o = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+                for (int j = 0; j < 4; ++j) o[j] = ok ? silu_gn_bf16x2(w[j], pa[j], pbh[j], pbl[j]) : 0u;
+                u[it] = make_uint4(o[0], o[1], o[2], o[3]);
+                continue;
               }
-              *slot = o;
+              float y[8];
+              float x[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { x[2 * j] = __uint_as_float(w[j] << 16); x[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+              {                     // LayerNorm (x Modulation)
+                const float mean = rowtab[2 * (r & 127)], rstd = rowtab[2 * (r & 127) + 1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = fmaf((x[j] - mean) * rstd, ca[j], cb[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) y[j] = ok ? y[j] : 0.f;
+              u[it] = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+            }
+#pragma unroll
+            for (int it = 0; it < 9; ++it) {
+              const int r = rsub + 16 * it;
+              if (r < rows_a) *reinterpret_cast<uint4*>(tile + r * 128 + ((g ^ (r & 7)) << 4)) = u[it];
             }
             fence_proxy_async();
           }
           mbar_arrive(&op_full[sa]);
+          if (tid == 0) SK_STAMP(2, 2 * ia + 1);
         }
       }
     }
   } else if (warp >= 8) {
-    // ------------------------------------------------------------- epilogue: one accumulator row per thread
+    // ------------------------------------------------------------- epilogue: 8 warps, one accumulator row per thread;
+    // the two warps of a TMEM lane quarter split every 32-column chunk into 16-column halves (two warps per SM
+    // sub-partition hide each other's TMEM / shared-memory latencies).
     const int q4 = warp & 3;
+    const int half = (warp - 8) >> 2;
     const int row = q4 * 32 + lane;
-    const int et = threadIdx.x - 256;          // 0..127
-    const bool elected = et == 0;
+    const int et = threadIdx.x - 256;          // 0..255
     const uint32_t lane_off = uint32_t(q4 * 32) << 16;
-    const int sw = row & 7;
+    const int resid_mode = p.resid_mode;
+    const bool has_out_r = p.has_out_r != 0, has_out_t = p.has_out_t != 0;
     float* ep_mul = sVEC;             // [BN] colscale
     float* ep_add = sVEC + BN;        // [BN] bias * colscale + rowvec
     float* ep_g = sVEC + 2 * BN;      // [BN] 1 + modulation scale   (resid_mode 2)
@@ -346,9 +389,9 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
         const int goff = (n0 / GS) & 7;
         if (b != cur_b || goff != cur_goff) flush_stats(cur_b, cur_goff);
         cur_goff = goff;
-        named_bar(2, 128);
+        named_bar(2, 256);
         cur_b = b; cur_n = n_idx;
-        for (int n = et; n < BN; n += 128) {
+        for (int n = et; n < BN; n += 256) {
           const int nm = (n0 + n) % p.bias_mod;
           const float cs = p.colscale ? p.colscale[(size_t)(b % p.cs_bmod) * p.cs_bstride + nm] : 1.f;
           const float rv = p.rowvec ? p.rowvec[(size_t)b * p.rowvec_stride + nm] : 0.f;
@@ -360,7 +403,7 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
             ep_sh[n] = md[p.N + n0 + n];
           }
         }
-        named_bar(2, 128);
+        named_bar(2, 256);
       }
       float r_mean = 0.f, r_rstd = 0.f;
       if (p.resid_mode == 2 && row_valid) {     // LayerNorm statistics of this thread's residual row
@@ -370,27 +413,41 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
         r_mean = a / (float)p.N;
         r_rstd = rsqrtf(fmaxf(c / (float)p.N - r_mean * r_mean, 0.f) + p.eps);
       }
+      if (et == 0) SK_STAMP(6, 2 * i);
       mbar_wait(&acc_full[acc], (i >> 1) & 1);
+      if (et == 0) SK_STAMP(6, 2 * i + 1);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + acc * BN + lane_off;
-      float rsum = 0.f, rsq = 0.f;
-      // One 32-column chunk.  The chunk loop below is deliberately NOT unrolled beyond a pair: the unrolled epilogue of
-      // a 256-wide tile is ~64 KB of SASS, which misses the instruction cache on every tile (ncu: stall_no_inst).
-      auto process = [&](const int c, const uint32_t (&v)[32]) {
-        const int c0 = c * 32;
+      const uint32_t tacc = tmem_base + acc * BN + lane_off + half * 16;
+      float rs0 = 0.f, rs1 = 0.f, rq0 = 0.f, rq1 = 0.f;
+      // One 32-column chunk; this WARP owns a [32 rows x 16 columns] sub-tile of it end to end: TMEM -> registers ->
+      // math -> its private slice of the staging buffers -> its own TMA stores.  There is no CTA-level barrier in the
+      // chunk loop (the eight epilogue warps drift freely and hide each other's latencies).  The loop is NOT unrolled
+      // beyond a pair: a fully unrolled epilogue is ~64 KB of SASS and misses the instruction cache on every tile.
+      auto process = [&](const int c, const uint32_t (&v)[16]) {
+        const int c0 = c * 32 + half * 16;         // first column of this thread's half inside the tile
         const int rs = q % NR;
-        uint8_t* rt = sR + rs * C::R_BYTES;
-        uint8_t* tt = sT + rs * C::T_BYTES;
+        uint8_t* rt = sR + rs * C::R_BYTES + half * (C::R_BYTES / 2);                       // [128 rows][64 B], 64B swizzle
+        uint8_t* tt = sT + (q % NT) * C::T_BYTES + (half * 4 + q4) * 1024;                   // [32 rows][32 B]
+        if (et == 0) SK_STAMP(4, 4 * q);
+        // this warp's stores of chunk q-2 no longer read shared memory -> its T slice (reused every NT = 2 chunks) and
+        // R slice are free again; chunk q-1's residual buffer goes back to the TMA producer once its store was read
+        if (lane == 0) {
+          bulk_wait_read<1>();
+          if (p.resid_mode != 0 && q > 1) mbar_arrive(&rc_empty[(q - 2) % NR]);
+        }
+        __syncwarp();
         if (p.resid_mode != 0) mbar_wait(&rc_full[rs], (q / NR) & 1);
-        float y[32];
+        if (et == 0) SK_STAMP(4, 4 * q + 1);
+        const int sw = (row >> 1) & 3;
+        float y[16];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
+        for (int j4 = 0; j4 < 4; ++j4) {
           const float4 mu = *reinterpret_cast<const float4*>(&ep_mul[c0 + j4 * 4]);
           const float4 ad = *reinterpret_cast<const float4*>(&ep_add[c0 + j4 * 4]);
-          uint8_t* slot = rt + row * 128 + ((j4 ^ sw) << 4);
+          uint8_t* slot = rt + row * 64 + ((j4 ^ sw) << 4);
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.resid_mode != 0) x = *reinterpret_cast<const float4*>(slot);
-          if (p.resid_mode == 2) {
+          if (resid_mode != 0) x = *reinterpret_cast<const float4*>(slot);
+          if (resid_mode == 2) {
             const float4 gg = *reinterpret_cast<const float4*>(&ep_g[c0 + j4 * 4]);
             const float4 sh = *reinterpret_cast<const float4*>(&ep_sh[c0 + j4 * 4]);
             x.x = fmaf((x.x - r_mean) * r_rstd, gg.x, sh.x); x.y = fmaf((x.y - r_mean) * r_rstd, gg.y, sh.y);
@@ -400,78 +457,80 @@ __global__ void __launch_bounds__(384, 1) sk_kernel(const __grid_constant__ SkPa
           y[j4 * 4 + 1] = fmaf(__uint_as_float(v[j4 * 4 + 1]), mu.y, ad.y) + x.y;
           y[j4 * 4 + 2] = fmaf(__uint_as_float(v[j4 * 4 + 2]), mu.z, ad.z) + x.z;
           y[j4 * 4 + 3] = fmaf(__uint_as_float(v[j4 * 4 + 3]), mu.w, ad.w) + x.w;
-          if (p.has_out_r) *reinterpret_cast<float4*>(slot) = make_float4(y[j4 * 4], y[j4 * 4 + 1], y[j4 * 4 + 2], y[j4 * 4 + 3]);
+          if (has_out_r) *reinterpret_cast<float4*>(slot) = make_float4(y[j4 * 4], y[j4 * 4 + 1], y[j4 * 4 + 2], y[j4 * 4 + 3]);
         }
-        if (p.has_out_t) {      // [128 rows][64 B], 64-byte swizzle: 16-byte chunk j ^ ((row >> 1) & 3)
+        if (has_out_t) {
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8)
-            *reinterpret_cast<uint4*>(tt + row * 64 + ((j8 ^ ((row >> 1) & 3)) << 4)) =
+          for (int j8 = 0; j8 < 2; ++j8)
+            *reinterpret_cast<uint4*>(tt + lane * 32 + j8 * 16) =
                 make_uint4(pack_bf16(y[j8 * 8], y[j8 * 8 + 1]), pack_bf16(y[j8 * 8 + 2], y[j8 * 8 + 3]),
                            pack_bf16(y[j8 * 8 + 4], y[j8 * 8 + 5]), pack_bf16(y[j8 * 8 + 6], y[j8 * 8 + 7]));
         }
         if (row_valid) {
           if (p.stats_out != nullptr) {
-            constexpr int NSB = GS >= 32 ? 1 : 32 / GS;      // sub-blocks of one group inside the chunk
-            constexpr int SBW = 32 / NSB;
-            float ps1[NSB], ps2[NSB];
+            constexpr int NSB = GS >= 16 ? 1 : 16 / GS;      // sub-blocks of one group inside the 16 columns
+            constexpr int SBW = 16 / NSB;
+            const int off = (c0 / GS) & 7;                   // local group of sub-block sb = (off + sb) & 7
 #pragma unroll
             for (int sb = 0; sb < NSB; ++sb) {
-              float a = 0.f, b2 = 0.f;
+              float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two independent chains per sum
 #pragma unroll
-              for (int j = 0; j < SBW; ++j) { a += y[sb * SBW + j]; b2 = fmaf(y[sb * SBW + j], y[sb * SBW + j], b2); }
-              ps1[sb] = a; ps2[sb] = b2;
-            }
-            if constexpr (NSB == 8) {      // GS = 4: the chunk holds all eight groups in order
+              for (int j = 0; j < SBW; j += 2) {
+                a0 += y[sb * SBW + j]; a1 += y[sb * SBW + j + 1];
+                b0 = fmaf(y[sb * SBW + j], y[sb * SBW + j], b0); b1 = fmaf(y[sb * SBW + j + 1], y[sb * SBW + j + 1], b1);
+              }
+              a0 += a1; b0 += b1;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) { s1[k] += ps1[k]; s2[k] += ps2[k]; }
-            } else {                       // local group of sub-block sb = (c0 / GS + sb) & 7: predicated scatter
-              const int off = (c0 / GS) & 7;
-#pragma unroll
-              for (int sb = 0; sb < NSB; ++sb)
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                  if (((off + sb) & 7) == k) { s1[k] += ps1[sb]; s2[k] += ps2[sb]; }
+              for (int k = 0; k < 8; ++k)
+                if (((off + sb) & 7) == k) { s1[k] += a0; s2[k] += b0; }
             }
           }
           if (p.rowstats_out != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { rsum += y[j]; rsq = fmaf(y[j], y[j], rsq); }
+            for (int j = 0; j < 16; j += 2) {
+              rs0 += y[j]; rs1 += y[j + 1];
+              rq0 = fmaf(y[j], y[j], rq0); rq1 = fmaf(y[j + 1], y[j + 1], rq1);
+            }
           }
         }
         if (c == NCH - 1) {           // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
         }
-        fence_proxy_async();
-        named_bar(1, 128);
-        if (elected) {
-          if (p.has_out_r) tma_store_3d(&p.tmR, rt, n0 + c0, l0, b);
-          if (p.has_out_t) tma_store_3d(&p.tmT, tt, n0 + c0, l0, b);
+        if (et == 0) SK_STAMP(4, 4 * q + 2);
+        fence_proxy_async();          // generic-proxy writes of this warp's slices -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          if (has_out_r) tma_store_3d(&p.tmRs, rt + q4 * 2048, n0 + c0, l0 + q4 * 32, b);
+          if (has_out_t) tma_store_3d(&p.tmT, tt, n0 + c0, l0 + q4 * 32, b);
           bulk_commit();
-          bulk_wait_read<1>();                               // the previous chunk's stores no longer read their buffers
-          if (p.resid_mode != 0 && q > 0) mbar_arrive(&rc_empty[(q - 1) % NR]);
+          if (et == 0) SK_STAMP(4, 4 * q + 3);
         }
         ++q;
       };
-      uint32_t v0[32], v1[32];
-      tmem_ld32(tacc, v0);
+      uint32_t v0[16], v1[16];
+      tmem_ld16(tacc, v0);
 #pragma unroll 1
       for (int c = 0; c < NCH; c += 2) {
         tmem_ld_wait();
-        tmem_ld32(tacc + (c + 1) * 32, v1);
+        tmem_ld16(tacc + (c + 1) * 32, v1);
         process(c, v0);
         tmem_ld_wait();
-        if (c + 2 < NCH) tmem_ld32(tacc + (c + 2) * 32, v0);
+        if (c + 2 < NCH) tmem_ld16(tacc + (c + 2) * 32, v0);
         process(c + 1, v1);
       }
-      if (p.rowstats_out != nullptr && row_valid) {
-        float* dst = p.rowstats_out + (((size_t)b * p.L + l0 + row) * p.n_tiles + n_idx) * 2;
-        dst[0] = rsum;
-        dst[1] = rsq;
+      if (p.rowstats_out != nullptr && row_valid) {      // two partial sums per (row, n tile): one per column half
+        float* dst = p.rowstats_out + (((size_t)b * p.L + l0 + row) * (2 * p.n_tiles) + 2 * n_idx + half) * 2;
+        dst[0] = rs0 + rs1;
+        dst[1] = rq0 + rq1;
       }
     }
     flush_stats(cur_b, cur_goff);
-    if (elected) bulk_wait<0>();
+    if (lane == 0) {                    // every thread that issued stores waits for its bulk groups before exit
+      if (et == 0) SK_STAMP(7, 1);
+      bulk_wait<0>();
+      if (et == 0) SK_STAMP(7, 2);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -498,7 +557,7 @@ inline cudaError_t sk_set_attrs() {
 inline void sk_launch(int id, const SkParams& p, int num_sms, cudaStream_t st) {
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   int i = 0;
-#define X(a, b) if (id == i++) { sk_kernel<a, b><<<grid, 384, SkCfg<a>::SMEM, st>>>(p); return; }
+#define X(a, b) if (id == i++) { sk_kernel<a, b><<<grid, 512, SkCfg<a>::SMEM, st>>>(p); return; }
   SFB_SK_LIST(X)
 #undef X
 }

@@ -1,7 +1,7 @@
 import json, sys, csv, collections
 d=json.load(open('gpurun_out/bench.json'))
 print("clips/s", round(d['value'],2), "ms/step", round(d['ms_per_step'],1), "e2e", round(d['e2e']['value'],2), "launches", d['gpu_launches'], d['clocks'])
-r=d['roofline']; print("gemm TF/s", round(r['achieved'],1), "frac", round(r['frac'],3), "e2e frac", round(r['end_to_end_frac_of_bf16_peak'],3))
+r=d["roofline"]; print("dominant kernel TF/s", round(r['achieved'],1), "frac", round(r['frac'],3), "e2e frac", round(r['end_to_end_frac_of_bf16_peak'],3))
 for k,v in r['per_kernel'].items(): print("  ", k, v)
 try:
     with open('gpurun_out/launches.csv') as f:
