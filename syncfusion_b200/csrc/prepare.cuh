@@ -87,4 +87,59 @@ __global__ void build_emb_rows_kernel(const float* __restrict__ emb, const float
   for (int k = threadIdx.x; k < F; k += blockDim.x) out[(size_t)r * F + k] = (r < B) ? emb[(size_t)r * F + k] : fixed[k];
 }
 
+
+// ---------------------------------------------------------------------------------------------------- LayerNorm fold
+// InjectChannels on a Modulation output (a7 + a8), with the per-position LayerNorm folded OUT of the GEMM operand
+// (sk_tc.cuh, SkParams::ln_fold):   W [ (LN(x) (1 + s) + sh) | ctx ] = rstd (W' x - mean ws) + Wc ctx + wsh
+//   W'[n, k] = bf16(W[n, k] (1 + s[k]))   ws[n] = sum_k W'[n, k]   wsh[n] = sum_k W[n, k] sh[k]        (k < C)
+// (1 + s, sh) change every sampler step (and per clip in unet_forward), so the scaled copy of every streaming-K inject
+// weight is rebuilt by ONE launch per U-Net evaluation: one warp per (copy, output row).  ~27 MB per copy.
+struct FoldItem {
+  const __nv_bfloat16* W;   // [N][K] (K = C + ctx), K-major
+  __nv_bfloat16* Wd;        // [copies][N][K]
+  float* vec;               // [copies][2 N]: ws | wsh
+  int C, K, N, mod_off, row0;
+};
+__global__ void __launch_bounds__(256) inject_fold_kernel(const FoldItem* __restrict__ items, int n_items, int total_rows,
+                                                          const float* __restrict__ frow, int bstride, int copies) {
+  const int gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= total_rows * copies) return;
+  const int copy = gw / total_rows, row = gw % total_rows;
+  int it = 0;
+  while (it + 1 < n_items && items[it + 1].row0 <= row) ++it;
+  const FoldItem f = items[it];
+  const int n = row - f.row0;
+  const float* md = frow + (size_t)copy * bstride + f.mod_off;     // scale [C] | shift [C]
+  const __nv_bfloat16* src = f.W + (size_t)n * f.K;
+  __nv_bfloat16* dst = f.Wd + ((size_t)copy * f.N + n) * f.K;
+  float ws = 0.f, wsh = 0.f;
+  for (int k = lane * 8; k < f.K; k += 256) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + k);
+    if (k < f.C) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w0 = __uint_as_float(w[j] << 16), w1 = __uint_as_float(w[j] & 0xFFFF0000u);
+        const float2 sc = *reinterpret_cast<const float2*>(md + k + 2 * j);
+        const float2 sh = *reinterpret_cast<const float2*>(md + f.C + k + 2 * j);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(w0 * (1.f + sc.x), w1 * (1.f + sc.y));
+        ws += __bfloat162float(h.x) + __bfloat162float(h.y);
+        wsh = fmaf(w0, sh.x, fmaf(w1, sh.y, wsh));
+        o[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(dst + k) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      *reinterpret_cast<uint4*>(dst + k) = u;      // context columns are not modulated
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { ws += __shfl_xor_sync(0xffffffffu, ws, o); wsh += __shfl_xor_sync(0xffffffffu, wsh, o); }
+  if (lane == 0) {
+    f.vec[(size_t)copy * 2 * f.N + n] = ws;
+    f.vec[(size_t)copy * 2 * f.N + f.N + n] = wsh;
+  }
+}
+
 }  // namespace sfb

@@ -118,6 +118,7 @@ struct ItemW {
   bool has_attn = false, has_xattn = false, has_inject = false;
   float *x_ng = nullptr, *x_nb = nullptr, *x_wv = nullptr, *x_wo = nullptr;
   int mod_off = 0, xb_off = 0;
+  float* qkv_ws = nullptr;   // [1536] column sums of the bf16 fused QKV weights (LayerNorm fold, sk_tc.cuh)
 };
 struct DepthW {
   GemmW down, up;
@@ -283,6 +284,7 @@ struct Engine : EngineBase {
     size_t sigma, embrows, tmp1, tmp2, fourier, h1, h2, feat, ftable, xbias, stats, stats_bytes, veff, xstate, total;
     size_t ctx[SFB_MAX_DEPTH], bufA[SFB_MAX_DEPTH], T1[SFB_MAX_DEPTH], T2[SFB_MAX_DEPTH], qkv[SFB_MAX_DEPTH], o[SFB_MAX_DEPTH];
     size_t rs1[SFB_MAX_DEPTH], rs2[SFB_MAX_DEPTH];   // per-position LayerNorm partial sums [rows, parts <= 8, 2] (sk path)
+    size_t foldw, foldw_bytes;                        // scaled inject weights + (ws | wsh) vectors, B copies (LayerNorm fold)
   };
   struct Plan {
     int64_t B = 0, L = 0;
@@ -570,6 +572,15 @@ struct Engine : EngineBase {
               bb[n] = (float)acc;
             }
             I.qkv.w = upload_T(r); I.qkv.bias = upload<float>(bb);
+            {
+              std::vector<float> wsum(3 * mid);
+              for (int n = 0; n < 3 * mid; ++n) {
+                double acc = 0;
+                for (int k = 0; k < C; ++k) acc += (double)(float)host_cvt<T>(r[(size_t)n * C + k]);
+                wsum[n] = (float)acc;
+              }
+              I.qkv_ws = upload<float>(wsum);
+            }
             I.qkv.N = 3 * mid; I.qkv.K1 = C; I.qkv.taps = 1; I.qkv.bias_mod = 3 * mid;
             I.out.w = upload_T(wo->v); I.out.bias = nullptr;
             I.out.N = C; I.out.K1 = mid; I.out.taps = 1; I.out.bias_mod = C;
@@ -651,8 +662,18 @@ struct Engine : EngineBase {
         w.qkv[d] = w.o[d] = 0;
       }
     }
+    w.foldw_bytes = 0;
+    for (int d = 0; d < cfg.depth; ++d)
+      if (depth_sk(d))
+        for (int s = 0; s < 2; ++s)
+          for (const ItemW& I : dw[d].items[s])
+            w.foldw_bytes += fold_item_bytes(I, B);
+    w.foldw = take(std::max<size_t>(w.foldw_bytes, 16));
     w.total = off;
   }
+  // scaled weight copies [B][N][K] bf16 + vectors [B][2 N] fp32 of one streaming-K inject item
+  static size_t fold_w_bytes(const ItemW& I, int64_t copies) { return align_up((size_t)copies * I.inject.N * (I.inject.K1 + I.inject.K2) * 2, 1024); }
+  static size_t fold_item_bytes(const ItemW& I, int64_t copies) { return fold_w_bytes(I, copies) + align_up((size_t)copies * 2 * I.inject.N * 4, 1024); }
   int workspace_bytes(int64_t B, int64_t L, int cfg_on, int64_t rows, size_t* out) override {
     if (!finalized) return fail(SFB_ERR_STATE, "finalize first");
     int64_t tf = 1;
@@ -717,7 +738,8 @@ struct Engine : EngineBase {
   }
   // Streaming-K fused GEMM (sk_tc.cuh).  gs_out: GroupNorm group size of the output statistics (0: none).
   bool sk_ok(const GemmW& g) const { return kBF16 && !no_sk && g.N % 128 == 0 && g.K1 % 64 == 0 && g.w != nullptr; }
-  bool add_sk(Op& op, const GemmW& g, const void* a1, int L, int Beff, const void* a2, int B2, int gs_out) {
+  bool add_sk(Op& op, const GemmW& g, const void* a1, int L, int Beff, const void* a2, int B2, int gs_out,
+              const void* w_override = nullptr, int w_copies = 1) {
     const int BN = g.N % 256 == 0 ? 256 : 128;
     int id = sk_find(BN, gs_out > 0 ? gs_out : (BN == 256 ? 32 : 16));
     if (id < 0) return false;
@@ -727,7 +749,9 @@ struct Engine : EngineBase {
     if (!make_tmap3<__nv_bfloat16>(&p.tmA1, a1, g.K1, L, Beff, 64, g.taps == 3 ? 136 : 128)) return false;
     if (g.K2 > 0) { if (!make_tmap3<__nv_bfloat16>(&p.tmA2, a2, g.K2, L, B2, 64, 128)) return false; }
     else p.tmA2 = p.tmA1;
-    if (!make_tmap2<__nv_bfloat16>(&p.tmW, g.w, (uint64_t)(g.K1 + g.K2), (uint64_t)g.taps * g.N, 64, BN)) return false;
+    if (!make_tmap3<__nv_bfloat16>(&p.tmW, w_override ? w_override : g.w, (uint64_t)(g.K1 + g.K2), (uint64_t)g.taps * g.N,
+                                   (uint64_t)w_copies, 64, BN)) return false;
+    p.w_bmod = 1;
     p.tmR = p.tmA1; p.tmRs = p.tmA1; p.tmT = p.tmA1;
     p.L = L; p.tiles_per_clip = (L + 127) / 128; p.N = g.N; p.n_tiles = g.N / BN;
     p.total_tiles = Beff * p.tiles_per_clip * p.n_tiles;
@@ -758,6 +782,10 @@ struct Engine : EngineBase {
   }
 
   // ---- streaming-K fused path (bf16, C % 128 == 0): every norm is folded into a GEMM prologue / epilogue -------------
+  std::vector<FoldItem> fold_items;   // streaming-K inject items of the current plan (LayerNorm fold)
+  FoldItem* fold_items_dev = nullptr;
+  size_t fold_next = 0, fold_items_cap = 0;
+  int fold_rows = 0;
   void* xt_cur[SFB_MAX_DEPTH] = {};   // bf16 copy of the tensor currently in bufA[d] (written by whoever produced it)
   bool depth_sk(int d) const {
     if (!kBF16 || no_sk || d == 0 || cfg.channels[d] % 128) return false;
@@ -806,9 +834,20 @@ struct Engine : EngineBase {
     int parts2;
     {  // inject: i = W [Mod(LN(r)) | ctx] + b + Mod(LN(r)) (+ cross-attention bias)  ->  bufA (fp32), P1 (bf16)
       Op o = base("inject"); o.in = P0; o.ft_off = I.mod_off; o.sk_ft_is_mod = 1; o.ctx = cfg.context_channels[d];
-      if (!add_sk(o, I.inject, P0, L, Beff, at<T>(plan.lay.ctx[d]), (int)B, last_is_inject && want_stats ? gs : 0) ||
+      // LayerNorm fold: the MMA reads the raw bf16 rows of r against W diag(1 + s) (rebuilt per evaluation by
+      // inject_fold_kernel), the context rows are pre-divided by rstd, the epilogue applies rstd (D - mean ws) + W sh.
+      uint8_t* fw = at<uint8_t>(plan.lay.foldw) + fold_next;
+      float* fvec = reinterpret_cast<float*>(fw + fold_w_bytes(I, B));
+      fold_next += fold_item_bytes(I, B);
+      FoldItem fi;
+      fi.W = reinterpret_cast<const __nv_bfloat16*>(I.inject.w); fi.Wd = reinterpret_cast<__nv_bfloat16*>(fw); fi.vec = fvec;
+      fi.C = C; fi.K = I.inject.K1 + I.inject.K2; fi.N = I.inject.N; fi.mod_off = I.mod_off; fi.row0 = fold_rows;
+      fold_rows += fi.N;
+      fold_items.push_back(fi);
+      if (!add_sk(o, I.inject, P0, L, Beff, at<T>(plan.lay.ctx[d]), (int)B, last_is_inject && want_stats ? gs : 0, fw, (int)B) ||
           !sk_out_r(o, A, 2) || !sk_out_t(o, P1)) return fail(SFB_ERR_CUDA, err_fmt, "inject", d);
-      o.sp.xf = 2; o.sp.rowstats_in = RS1; o.sp.rs_parts = parts1;
+      o.sp.xf = 3; o.sp.ln_fold = 1; o.sp.ws = fvec; o.sp.addvec = fvec + I.inject.N; o.sp.ws_bstride = 2 * I.inject.N;
+      o.sp.rowstats_in = RS1; o.sp.rs_parts = parts1;
       if (last_is_inject) {
         o.stats_out = sOut; o.sp.stats_out = sOut;
         if (xb) { o.sp.rowvec = xb; o.sp.rowvec_stride = XB_total; }
@@ -825,7 +864,7 @@ struct Engine : EngineBase {
       {  // fused pre-norm + QKV projection (both LayerNorm affines are folded into W_qkv)
         Op o = base("qkv"); o.in = P1;
         if (!add_sk(o, I.qkv, P1, L, Beff, nullptr, 0, 0) || !sk_out_t(o, QKV)) return fail(SFB_ERR_CUDA, err_fmt, "qkv", d);
-        o.sp.xf = 2; o.sp.rowstats_in = RS2; o.sp.rs_parts = parts2;
+        o.sp.xf = 0; o.sp.ln_fold = 1; o.sp.ws = I.qkv_ws; o.sp.ws_bstride = 0; o.sp.rowstats_in = RS2; o.sp.rs_parts = parts2;
         set_dbg(o, rows, 1536); plan.ops.push_back(o);
       }
       {
@@ -1151,8 +1190,21 @@ struct Engine : EngineBase {
     plan.B = B; plan.L = L; plan.cfg_on = cfg_on; plan.ws = base; plan.lay = lay;
     wsb = base;
     stats_next = 0;
+    fold_items.clear(); fold_next = 0; fold_rows = 0;
     rc = build_block(0);
     if (rc) { plan.ops.clear(); return rc; }
+    if (!fold_items.empty()) {
+      if (fold_items.size() > fold_items_cap) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, fold_items.size() * sizeof(FoldItem)) != cudaSuccess) { plan.ops.clear(); return fail(SFB_ERR_CUDA, "fold table alloc"); }
+        owned.push_back(d);
+        fold_items_dev = reinterpret_cast<FoldItem*>(d); fold_items_cap = fold_items.size();
+      }
+      if (cudaMemcpy(fold_items_dev, fold_items.data(), fold_items.size() * sizeof(FoldItem), cudaMemcpyHostToDevice) != cudaSuccess) {
+        plan.ops.clear();
+        return fail(SFB_ERR_CUDA, "fold table upload");
+      }
+    }
     return SFB_OK;
   }
   int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes) override {
@@ -1191,6 +1243,12 @@ struct Engine : EngineBase {
     const int Bx = (int)plan.B;
     SFB_CUDA(cudaMemsetAsync(at<double>(plan.lay.stats), 0, plan.lay.stats_bytes, st));
     ++launches;
+    if (!fold_items.empty()) {     // per-evaluation scaled inject weights (LayerNorm fold): one warp per (copy, row)
+      const size_t warps = (size_t)fold_rows * sc.bmod;
+      inject_fold_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(fold_items_dev, (int)fold_items.size(), fold_rows, sc.frow,
+                                                                     sc.bstride, sc.bmod);
+      ++launches;
+    }
     int n = (int)plan.ops.size();
     if (op_limit >= 0 && op_limit < n) n = op_limit;
     if (profiling && prof_ev.size() < 2 * plan.ops.size()) {
@@ -1258,7 +1316,7 @@ struct Engine : EngineBase {
           if constexpr (kBF16) {
             SkParams p = o.sp;
             if (o.ft_off >= 0) {
-              if (o.sk_ft_is_mod) { p.mod = sc.frow + o.ft_off; p.mod_bstride = sc.bstride; p.mod_bmod = sc.bmod; }
+              if (o.sk_ft_is_mod) { p.mod = sc.frow + o.ft_off; p.mod_bstride = sc.bstride; p.mod_bmod = sc.bmod; p.w_bmod = sc.bmod; }
               else { p.colscale = sc.frow + o.ft_off; p.cs_bstride = sc.bstride; p.cs_bmod = sc.bmod; }
             }
             sk_launch(o.sk_id, p, num_sms(), st);

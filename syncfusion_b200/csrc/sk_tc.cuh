@@ -24,12 +24,13 @@ namespace sfb {
 struct SkParams {
   CUtensorMap tmA1;   // bf16 [K1, L, B]    box [64, 136 | 128, 1]
   CUtensorMap tmA2;   // bf16 [K2, L, B2]   box [64, 128, 1]
-  CUtensorMap tmW;    // bf16 [K1 + K2, taps * N] box [64, BN]
+  CUtensorMap tmW;    // bf16 [K1 + K2, taps * N, copies] box [64, BN, 1]; copy = b % w_bmod (per-step / per-clip scaled weights)
   CUtensorMap tmR;    // fp32 [N, L, B]     box [16, 128, 1], 64-byte swizzle   residual in (two loads per 32-column chunk)
   CUtensorMap tmRs;   // fp32 [N, L, B]     box [16, 32, 1],  64-byte swizzle   fp32 out (one store per epilogue warp)
   CUtensorMap tmT;    // bf16 [N, L, B]     box [16, 32, 1],  no swizzle        bf16 out (one store per epilogue warp)
   // A transform
-  int xf;                       // 0 none, 1 GroupNorm + SiLU, 2 LayerNorm (x Modulation when mod != null)
+  int xf;                       // 0 none, 1 GroupNorm + SiLU, 2 LayerNorm (x Modulation when mod != null),
+                                // 3 A2 rows / rstd (the context half of a LayerNorm-folded inject, see ln_fold)
   const double* stats_in;       // [B, 8, 2] group sums of A1 (xf == 1)
   const float *gamma, *beta;    // [K1]
   const float* rowstats_in;     // [B * L, rs_parts, 2] partial (sum, sum of squares) of every A1 / residual row
@@ -42,6 +43,13 @@ struct SkParams {
   const float* rowvec;          // [B, rowvec_stride] or null
   int bias_mod, cs_bstride, cs_bmod, rowvec_stride;
   int resid_mode;               // 0 none, 1 + resid, 2 + LayerNorm/Modulation(resid)
+  // LayerNorm folded out of the A operand: W LN(x) = rstd (W x - mean W 1), so the MMA runs on the RAW bf16 rows and
+  // the accumulator is fixed per row in the epilogue: D' = rstd_l (D - mean_l ws[n]).  A Modulation scale lives in
+  // the weights (W diag(1 + s), rebuilt per step by inject_fold_kernel), its shift in addvec = W sh.
+  int ln_fold;
+  int w_bmod, ws_bstride;       // weight copy / ws / addvec row = (b % w_bmod) (* ws_bstride)
+  const float* ws;              // [copies][ws_bstride] sum_k W[n, k < K1]  (of the bf16 weights the MMA reads)
+  const float* addvec;          // [copies][ws_bstride] extra additive column vector or null
   int has_out_r, has_out_t;
   double* stats_out;            // [B, 8, 2] group sums of the output (group = (n / GS) % 8) or null
   float* rowstats_out;          // [B * L, n_tiles, 2] or null
@@ -69,7 +77,7 @@ template <int BN> struct SkCfg {
   static constexpr int OFF_TAB = OFF_T + NT * T_BYTES;         // [2][KMAX] per-channel transform coefficients
   static constexpr int OFF_ROWTAB = OFF_TAB + 2 * KMAX * 4;    // [136][2] per-row mean, rstd
   static constexpr int OFF_VEC = OFF_ROWTAB + 2 * 136 * 4 + 64;
-  static constexpr int OFF_BAR = OFF_VEC + 4 * BN * 4;
+  static constexpr int OFF_BAR = OFF_VEC + 5 * BN * 4;
   static constexpr int SMEM = OFF_BAR + 512;
   static constexpr int kThreads = 512;
   static_assert(SMEM <= 232448, "shared memory budget");
@@ -132,6 +140,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         const int mi = t / p.n_tiles;
         const int b = mi / p.tiles_per_clip;
         const int l0 = (mi % p.tiles_per_clip) * 128;
+        const int wcopy = b % p.w_bmod;
         for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
           const bool second = kc >= p.k1_chunks;
           const int sa = ia % NA;
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
             const int sb = ib % NB;
             mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
             mbar_expect_tx(&b_full[sb], C::B_BYTES);
-            tma_load_2d(sB + sb * C::B_BYTES, &p.tmW, &b_full[sb], second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64, tap * p.N + n0);
+            tma_load_3d(sB + sb * C::B_BYTES, &p.tmW, &b_full[sb], second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64, tap * p.N + n0, wcopy);
             SK_STAMP(1, ib);
           }
         }
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
             for (int c2 = tid, k = 0; c2 < p.K1 / 2; c2 += 128, ++k) {
               tabp[c2] = pk[0][k]; tabp[C::KMAX / 2 + c2] = pk[1][k]; tabp[C::KMAX + c2] = pk[2][k];
             }
-          } else {
+          } else if (p.xf == 2) {
             const float* md = p.mod ? p.mod + (size_t)(b % p.mod_bmod) * p.mod_bstride : nullptr;
             for (int c = tid; c < p.K1; c += 128) {
               tab_a[c] = md ? 1.f + md[c] : 1.f;
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           }
           named_bar(3, 128);
         }
-        if (p.xf == 2 && mi != cur_mi) {   // per-position LayerNorm statistics of this M tile's rows
+        if (p.xf >= 2 && mi != cur_mi) {   // per-position LayerNorm statistics of this M tile's rows
           cur_mi = mi;
           named_bar(3, 128);
           {
@@ -268,7 +277,8 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
               float s1 = 0.f, s2 = 0.f;
               for (int j = 0; j < p.rs_parts; ++j) { s1 += rsrc[2 * j]; s2 += rsrc[2 * j + 1]; }
               mean = s1 / (float)p.K1;
-              rstd = rsqrtf(fmaxf(s2 / (float)p.K1 - mean * mean, 0.f) + p.eps);
+              const float var = fmaxf(s2 / (float)p.K1 - mean * mean, 0.f) + p.eps;
+              rstd = p.xf == 3 ? sqrtf(var) : rsqrtf(var);       // xf 3 scales the context rows by 1 / rstd
             }
             rowtab[2 * tid] = mean;
             rowtab[2 * tid + 1] = rstd;
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           const int sa = ia % NA;
           mbar_wait(&a_full[sa], (ia / NA) & 1);
           if (tid == 0) SK_STAMP(2, 2 * ia);
-          if (kc < p.k1_chunks) {
+          if (p.xf == 3 ? kc >= p.k1_chunks : kc < p.k1_chunks) {
             uint8_t* tile = sA + sa * C::A_BYTES;
             float ca[8], cb[8];
             uint32_t pa[4], pbh[4], pbl[4];
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
               pa[0] = q0.x; pa[1] = q0.y; pa[2] = q0.z; pa[3] = q0.w;
               pbh[0] = q1.x; pbh[1] = q1.y; pbh[2] = q1.z; pbh[3] = q1.w;
               pbl[0] = q2.x; pbl[1] = q2.y; pbl[2] = q2.z; pbl[3] = q2.w;
-            } else {
+            } else if (p.xf == 2) {
               const float4 a0 = *reinterpret_cast<const float4*>(&tab_a[kc * 64 + g * 8]), a1 = *reinterpret_cast<const float4*>(&tab_a[kc * 64 + g * 8 + 4]);
               const float4 b0 = *reinterpret_cast<const float4*>(&tab_b[kc * 64 + g * 8]), b1 = *reinterpret_cast<const float4*>(&tab_b[kc * 64 + g * 8 + 4]);
               ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
@@ -320,10 +330,14 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
               float x[8];
 #pragma unroll
               for (int j = 0; j < 4; ++j) { x[2 * j] = __uint_as_float(w[j] << 16); x[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
-              {                     // LayerNorm (x Modulation)
+              if (p.xf == 2) {      // LayerNorm (x Modulation)
                 const float mean = rowtab[2 * (r & 127)], rstd = rowtab[2 * (r & 127) + 1];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) y[j] = fmaf((x[j] - mean) * rstd, ca[j], cb[j]);
+              } else {              // context rows / rstd (ln_fold multiplies the whole accumulator row by rstd)
+                const float isd = rowtab[2 * (r & 127) + 1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = x[j] * isd;
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) y[j] = ok ? y[j] : 0.f;
@@ -356,6 +370,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
     float* ep_add = sVEC + BN;        // [BN] bias * colscale + rowvec
     float* ep_g = sVEC + 2 * BN;      // [BN] 1 + modulation scale   (resid_mode 2)
     float* ep_sh = sVEC + 3 * BN;     // [BN] modulation shift
+    float* ep_ws = sVEC + 4 * BN;     // [BN] weight column sums (ln_fold)
     float s1[8], s2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
@@ -395,8 +410,10 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           const int nm = (n0 + n) % p.bias_mod;
           const float cs = p.colscale ? p.colscale[(size_t)(b % p.cs_bmod) * p.cs_bstride + nm] : 1.f;
           const float rv = p.rowvec ? p.rowvec[(size_t)b * p.rowvec_stride + nm] : 0.f;
+          const size_t wrow = (size_t)(b % p.w_bmod) * p.ws_bstride + n0 + n;
           ep_mul[n] = cs;
-          ep_add[n] = (p.bias ? p.bias[nm] : 0.f) * cs + rv;
+          ep_add[n] = ((p.bias ? p.bias[nm] : 0.f) + (p.addvec ? p.addvec[wrow] : 0.f)) * cs + rv;
+          if (p.ln_fold) ep_ws[n] = p.ws[wrow];
           if (p.resid_mode == 2) {
             const float* md = p.mod + (size_t)(b % p.mod_bmod) * p.mod_bstride;
             ep_g[n] = 1.f + md[n0 + n];
@@ -406,13 +423,15 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         named_bar(2, 256);
       }
       float r_mean = 0.f, r_rstd = 0.f;
-      if (p.resid_mode == 2 && row_valid) {     // LayerNorm statistics of this thread's residual row
+      if ((p.resid_mode == 2 || p.ln_fold) && row_valid) {     // LayerNorm statistics of this thread's A1 / residual row
         const float* rsrc = p.rowstats_in + ((size_t)b * p.L + l0 + row) * p.rs_parts * 2;
         float a = 0.f, c = 0.f;
         for (int j = 0; j < p.rs_parts; ++j) { a += rsrc[2 * j]; c += rsrc[2 * j + 1]; }
-        r_mean = a / (float)p.N;
-        r_rstd = rsqrtf(fmaxf(c / (float)p.N - r_mean * r_mean, 0.f) + p.eps);
+        r_mean = a / (float)p.K1;
+        r_rstd = rsqrtf(fmaxf(c / (float)p.K1 - r_mean * r_mean, 0.f) + p.eps);
       }
+      const bool ln_fold = p.ln_fold != 0;
+      const float f_mul = ln_fold ? r_rstd : 1.f, f_sub = ln_fold ? -r_rstd * r_mean : 0.f;
       if (et == 0) SK_STAMP(6, 2 * i);
       mbar_wait(&acc_full[acc], (i >> 1) & 1);
       if (et == 0) SK_STAMP(6, 2 * i + 1);
@@ -453,10 +472,17 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
             x.x = fmaf((x.x - r_mean) * r_rstd, gg.x, sh.x); x.y = fmaf((x.y - r_mean) * r_rstd, gg.y, sh.y);
             x.z = fmaf((x.z - r_mean) * r_rstd, gg.z, sh.z); x.w = fmaf((x.w - r_mean) * r_rstd, gg.w, sh.w);
           }
-          y[j4 * 4 + 0] = fmaf(__uint_as_float(v[j4 * 4 + 0]), mu.x, ad.x) + x.x;
-          y[j4 * 4 + 1] = fmaf(__uint_as_float(v[j4 * 4 + 1]), mu.y, ad.y) + x.y;
-          y[j4 * 4 + 2] = fmaf(__uint_as_float(v[j4 * 4 + 2]), mu.z, ad.z) + x.z;
-          y[j4 * 4 + 3] = fmaf(__uint_as_float(v[j4 * 4 + 3]), mu.w, ad.w) + x.w;
+          float d0 = __uint_as_float(v[j4 * 4 + 0]), d1 = __uint_as_float(v[j4 * 4 + 1]);
+          float d2 = __uint_as_float(v[j4 * 4 + 2]), d3 = __uint_as_float(v[j4 * 4 + 3]);
+          if (ln_fold) {            // D' = rstd (D - mean ws[n])
+            const float4 wsv = *reinterpret_cast<const float4*>(&ep_ws[c0 + j4 * 4]);
+            d0 = fmaf(f_mul, d0, f_sub * wsv.x); d1 = fmaf(f_mul, d1, f_sub * wsv.y);
+            d2 = fmaf(f_mul, d2, f_sub * wsv.z); d3 = fmaf(f_mul, d3, f_sub * wsv.w);
+          }
+          y[j4 * 4 + 0] = fmaf(d0, mu.x, ad.x) + x.x;
+          y[j4 * 4 + 1] = fmaf(d1, mu.y, ad.y) + x.y;
+          y[j4 * 4 + 2] = fmaf(d2, mu.z, ad.z) + x.z;
+          y[j4 * 4 + 3] = fmaf(d3, mu.w, ad.w) + x.w;
           if (has_out_r) *reinterpret_cast<float4*>(slot) = make_float4(y[j4 * 4], y[j4 * 4 + 1], y[j4 * 4 + 2], y[j4 * 4 + 3]);
         }
         if (has_out_t) {

@@ -10,7 +10,11 @@ ref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_
 ncu) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 125 -c 420 --csv --log-file gpurun_out/launches.csv python tools/ncu_step.py --steps 2 > gpurun_out/ncu_step.log 2>&1; tail -n 3 gpurun_out/ncu_step.log;;
 ncufull32) timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'gemm_tc_kernel<__nv_bfloat16, .int.32>' -s 1 -c 2 -f -o gpurun_out/prof_gemm32 python tools/ncu_step.py --steps 1 > gpurun_out/ncu_full32.log 2>&1; tail -n 2 gpurun_out/ncu_full32.log;;
 ncufull256) timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'gemm_tc_kernel<__nv_bfloat16, .int.256>' -s 20 -c 2 -f -o gpurun_out/prof_gemm256 python tools/ncu_step.py --steps 1 > gpurun_out/ncu_full256.log 2>&1; tail -n 2 gpurun_out/ncu_full256.log;;
-ncuattn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -s 0 -c 1 -f -o gpurun_out/prof_attn python tools/ncu_step.py --steps 1 > gpurun_out/ncu_attn.log 2>&1; tail -n 2 gpurun_out/ncu_attn.log;;
+ncuattn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -s 0 -c 1 -f -o gpurun_out/prof_attn python tools/ncu_step.py --steps 1 > gpurun_out/ncu_attn.log 2>&1; tail -n 2 gpurun_out/ncu_attn.log; ls -la gpurun_out;;
+opprof) timeout 600 python tools/op_profile.py > gpurun_out/op_profile.txt 2> gpurun_out/op_profile.err; tail -n 45 gpurun_out/op_profile.txt;;
+ncusk) timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats --section Occupancy --section SchedulerStats --clock-control none -k regex:sk_kernel -s 123 -c 123 -f -o gpurun_out/prof_sk python tools/ncu_step.py --steps 2 > gpurun_out/ncu_sk.log 2>&1; tail -n 2 gpurun_out/ncu_sk.log
+  ncu -i gpurun_out/prof_sk.ncu-rep --page raw --csv > gpurun_out/prof_sk_raw.csv 2>/dev/null; rm -f gpurun_out/prof_sk.ncu-rep; ls -la gpurun_out;;
+timeline) timeout 600 python tools/sk_timeline.py --ops "${SK_OPS:-4:out,6:qkv,6:conv1,7:inject}" > gpurun_out/sk_timeline.txt 2>&1; tail -n 3 gpurun_out/sk_timeline.txt;;
 smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; tail -n 5 gpurun_out/smoke.log;;
 esac
 done
