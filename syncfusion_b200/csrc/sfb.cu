@@ -22,6 +22,7 @@
 #include "prepare.cuh"
 #include "rk_tc.cuh"
 #include "sk_tc.cuh"
+#include "sk2_tc.cuh"
 
 using namespace sfb;
 
@@ -254,6 +255,7 @@ struct Engine : EngineBase {
   int F_total = 0, XB_total = 0, n_gn = 0;
   bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aids: force the unfused generic path
   bool no_sk = getenv("SFB_NO_SK") != nullptr;
+  bool no_sk2 = getenv("SFB_SK2") == nullptr;     // SFB_SK2=1: CTA-pair streaming-K kernel (sk2_tc.cuh) instead of the single-CTA one
 
   struct Op {
     int kind = 0, depth = 0, stack = 0, item = 0;
@@ -370,6 +372,7 @@ struct Engine : EngineBase {
     if (set_kernel_attrs<T>() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (kBF16 && rk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (rk) failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (kBF16 && sk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (sk) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (kBF16 && sk2_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (sk2) failed: %s", cudaGetErrorString(cudaGetLastError()));
 
     // time conditioning (A.3)
     t_w = upload_f(get("time.weights", {128}));
@@ -750,7 +753,7 @@ struct Engine : EngineBase {
     if (g.K2 > 0) { if (!make_tmap3<__nv_bfloat16>(&p.tmA2, a2, g.K2, L, B2, 64, 128)) return false; }
     else p.tmA2 = p.tmA1;
     if (!make_tmap3<__nv_bfloat16>(&p.tmW, w_override ? w_override : g.w, (uint64_t)(g.K1 + g.K2), (uint64_t)g.taps * g.N,
-                                   (uint64_t)w_copies, 64, BN)) return false;
+                                   (uint64_t)w_copies, 64, no_sk2 ? BN : BN / 2)) return false;
     p.w_bmod = 1;
     p.tmR = p.tmA1; p.tmRs = p.tmA1; p.tmT = p.tmA1;
     p.L = L; p.tiles_per_clip = (L + 127) / 128; p.N = g.N; p.n_tiles = g.N / BN;
@@ -767,13 +770,13 @@ struct Engine : EngineBase {
     op.out_r = ptr; op.sp.has_out_r = 1; op.sp.resid_mode = resid_mode;
     if (resid_mode) op.resid = ptr;
     op.bytes += (double)op.B * op.L * op.sp.N * (resid_mode ? 8 : 4);
-    return make_tmap3<float>(&op.sp.tmR, ptr, op.sp.N, op.L, op.B, 16, 128, CU_TENSOR_MAP_SWIZZLE_64B) &&
-           make_tmap3<float>(&op.sp.tmRs, ptr, op.sp.N, op.L, op.B, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    return make_tmap3<float>(&op.sp.tmR, ptr, op.sp.N, op.L, op.B, 32, 128, CU_TENSOR_MAP_SWIZZLE_128B) &&
+           make_tmap3<float>(&op.sp.tmRs, ptr, op.sp.N, op.L, op.B, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   }
   bool sk_out_t(Op& op, void* ptr) {
     op.out_t = ptr; op.sp.has_out_t = 1;
     op.bytes += (double)op.B * op.L * op.sp.N * 2;
-    return make_tmap3<__nv_bfloat16>(&op.sp.tmT, ptr, op.sp.N, op.L, op.B, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+    return make_tmap3<__nv_bfloat16>(&op.sp.tmT, ptr, op.sp.N, op.L, op.B, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   }
   void set_dbg(Op& op, int rows, int cols) {
     if (op.out_r) { op.dbg_off = (uint8_t*)op.out_r - wsb; op.dbg_dtype = 0; op.dbg_bytes = (size_t)rows * cols * 4; }
@@ -1319,7 +1322,8 @@ struct Engine : EngineBase {
               if (o.sk_ft_is_mod) { p.mod = sc.frow + o.ft_off; p.mod_bstride = sc.bstride; p.mod_bmod = sc.bmod; p.w_bmod = sc.bmod; }
               else { p.colscale = sc.frow + o.ft_off; p.cs_bstride = sc.bstride; p.cs_bmod = sc.bmod; }
             }
-            sk_launch(o.sk_id, p, num_sms(), st);
+            if (no_sk2) sk_launch(o.sk_id, p, num_sms(), st);
+            else sk2_launch(o.sk_id, p, num_sms(), st);
           }
           break;
         }

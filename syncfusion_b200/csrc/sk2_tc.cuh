@@ -1,72 +1,30 @@
-// Streaming-K fused tcgen05 implicit-GEMM for the tensor-bound depths (C >= 128), bf16 operands.
+// CTA-pair variant of the streaming-K fused tcgen05 implicit GEMM (sk_tc.cuh): cluster of two CTAs on one TPC,
+// tcgen05.mma.cta_group::2 with M = 256 over the pair.
 //
-//   D[b, l, n] = sum_{tap, k} f(A1)[b, l + tap - pad, k] W[tap N + n, k]  +  sum_k A2[b % m, l, k] W[n, K1 + k]
-//   out        = colscale[n'] (D + bias[n']) + rowvec[b, n'] + g(resid)                    n' = n % bias_mod
+// Each CTA keeps everything of ITS 128-row M tile exactly as the single-CTA kernel does (A ring + in-place transform,
+// residual ring, TMEM accumulators, epilogue, output statistics, TMA stores) but holds only HALF of every weight tile
+// (BN / 2 rows): the pair's tensor cores read both halves.  Per CTA that halves the L2 -> shared-memory weight traffic,
+// the shared-memory bytes of a weight stage (deeper rings in the same 227 KB) and the shared-memory read bandwidth
+// the MMA needs for B - the three things the single-CTA kernel runs out of (profiles/: tensor pipe 25-43 % active
+// with L2 and DRAM far from saturated).
 //
-// f = none | GroupNorm(8)+SiLU (ResNet convs, a6) | per-position LayerNorm (x Modulation) (inject a7/a8, QKV pre-norm a9)
-// g = none | identity | LayerNorm/Modulation recomputed in fp32 (InjectChannels adds the MODULATED tensor, which is
-// never stored).  So the GroupNorm / Modulation / pre-norm passes of the reference do not exist as kernels: the
-// statistics they need (fp64 group sums per clip, fp32 row sums per position) are emitted by the PRODUCER's epilogue.
-//
-// Persistent, warp-specialised, 128 x BN output tiles (n fastest), fp32 accumulators double-buffered in TMEM:
-//   warp 0      TMA producer (mainloop): A ring of [136 x 64] bf16 tiles - ONE load per K chunk serves all three conv
-//               taps (row-shifted UMMA descriptors, +128 B per tap) - and a B ring of [BN x 64] weight tiles
-//   warp 1      tcgen05.mma issuer
-//   warp 2      TMA producer (epilogue): residual chunks [128 x 32] fp32 into the R ring
-//   warps 4-7   A transform in place on the landed tile (fence.proxy.async before the MMA sees it)
-//   warps 8-11  epilogue, one accumulator row per thread, 32-column chunks: TMEM -> regs -> math -> fp32 chunk written
-//               IN PLACE over the residual chunk + bf16 chunk -> TMA stores; output statistics on the fly.
+//   rank 0 (leader) warp 1 : the only MMA issuer; waits  op_full (A of BOTH CTAs ready)  and  b_full (both halves landed)
+//   both ranks warp 0      : TMA producer; A -> local a_full, B half -> the LEADER's b_full (cta_group::2 load)
+//   both ranks warps 4-7   : A transform (or plain forwarding when xf == 0), then arrive on the LEADER's op_full
+//   both ranks warps 8-15  : epilogue of the own M tile; accumulator hand-back arrives on the LEADER's acc_empty
+//   tcgen05.commit.cta_group::2 multicasts a_empty / b_empty / acc_full to both CTAs.
 #pragma once
-#include "rk_tc.cuh"
+#include "sk_tc.cuh"
 
 namespace sfb {
 
-struct SkParams {
-  CUtensorMap tmA1;   // bf16 [K1, L, B]    box [64, 136 | 128, 1]
-  CUtensorMap tmA2;   // bf16 [K2, L, B2]   box [64, 128, 1]
-  CUtensorMap tmW;    // bf16 [K1 + K2, taps * N, copies] box [64, BN, 1]; copy = b % w_bmod (per-step / per-clip scaled weights)
-  CUtensorMap tmR;    // fp32 [N, L, B]     box [32, 128, 1], 128-byte swizzle  residual in (one load per 32-column chunk)
-  CUtensorMap tmRs;   // fp32 [N, L, B]     box [32, 32, 1],  128-byte swizzle  fp32 out (one store per epilogue warp and chunk)
-  CUtensorMap tmT;    // bf16 [N, L, B]     box [32, 32, 1],  64-byte swizzle   bf16 out (one store per epilogue warp and chunk)
-  // A transform
-  int xf;                       // 0 none, 1 GroupNorm + SiLU, 2 LayerNorm (x Modulation when mod != null),
-                                // 3 A2 rows / rstd (the context half of a LayerNorm-folded inject, see ln_fold)
-  const double* stats_in;       // [B, 8, 2] group sums of A1 (xf == 1)
-  const float *gamma, *beta;    // [K1]
-  const float* rowstats_in;     // [B * L, rs_parts, 2] partial (sum, sum of squares) of every A1 / residual row
-  int rs_parts;
-  const float* mod;             // [2 * K1] Modulation scale | shift of this step, row (b % mod_bmod) * mod_bstride
-  int mod_bstride, mod_bmod;
-  // epilogue
-  const float* bias;            // [bias_mod] or null
-  const float* colscale;        // [bias_mod] or null, row (b % cs_bmod) * cs_bstride
-  const float* rowvec;          // [B, rowvec_stride] or null
-  int bias_mod, cs_bstride, cs_bmod, rowvec_stride;
-  int resid_mode;               // 0 none, 1 + resid, 2 + LayerNorm/Modulation(resid)
-  // LayerNorm folded out of the A operand: W LN(x) = rstd (W x - mean W 1), so the MMA runs on the RAW bf16 rows and
-  // the accumulator is fixed per row in the epilogue: D' = rstd_l (D - mean_l ws[n]).  A Modulation scale lives in
-  // the weights (W diag(1 + s), rebuilt per step by inject_fold_kernel), its shift in addvec = W sh.
-  int ln_fold;
-  int w_bmod, ws_bstride;       // weight copy / ws / addvec row = (b % w_bmod) (* ws_bstride)
-  const float* ws;              // [copies][ws_bstride] sum_k W[n, k < K1]  (of the bf16 weights the MMA reads)
-  const float* addvec;          // [copies][ws_bstride] extra additive column vector or null
-  int has_out_r, has_out_t;
-  double* stats_out;            // [B, 8, 2] group sums of the output (group = (n / GS) % 8) or null
-  float* rowstats_out;          // [B * L, n_tiles, 2] or null
-  int L, tiles_per_clip, N, n_tiles, total_tiles, taps, k1_chunks, k2_chunks, K1, a2_bmod;
-  float eps;
-  long long* dbg;               // optional timeline buffer (CTA 0 only): [role][256] clock64 stamps (tools/sk_timeline.py)
-};
-
-#define SK_STAMP(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
-
-template <int BN> struct SkCfg {
-  static constexpr int NA = BN == 256 ? 2 : 3;
-  static constexpr int NB = BN == 256 ? 3 : 5;
+template <int BN> struct Sk2Cfg {
+  static constexpr int NA = 3;
+  static constexpr int NB = BN == 256 ? 5 : 6;
   static constexpr int NR = 4;                 // residual / fp32-out chunk ring (in place)
   static constexpr int NT = 2;                 // bf16-out chunk ring
   static constexpr int A_BYTES = 136 * 128;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = (BN / 2) * 128;   // this CTA's half of a [BN x 64] weight tile
   static constexpr int R_BYTES = 128 * 128;    // [128 rows][32 fp32], 128B swizzle
   static constexpr int T_BYTES = 128 * 64;     // [4 lane quarters][32 rows][32 bf16], 64B swizzle, one per chunk parity
   static constexpr int KMAX = 1024;            // largest transformed K1
@@ -84,8 +42,8 @@ template <int BN> struct SkCfg {
 };
 
 template <int BN, int GS>
-__global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkParams p) {
-  using C = SkCfg<BN>;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) sk2_kernel(const __grid_constant__ SkParams p) {
+  using C = Sk2Cfg<BN>;
   constexpr int NA = C::NA, NB = C::NB, NR = C::NR, NT = C::NT;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + C::OFF_A;
@@ -109,8 +67,12 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rc_empty + NR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t_begin = (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
-  const int t_end = (int)(((long long)p.total_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const uint32_t rank = cluster_ctarank();           // 0: leader (issues the MMAs), 1: peer
+  const int pairs_per_clip = (p.tiles_per_clip + 1) / 2;
+  const int total_pt = (p.total_tiles / (p.tiles_per_clip * p.n_tiles)) * pairs_per_clip * p.n_tiles;   // pair tiles
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int t_begin = (int)(((long long)total_pt * pair) / npairs);
+  const int t_end = (int)(((long long)total_pt * (pair + 1)) / npairs);
   const int pad = p.taps == 3 ? 1 : 0;
   const int rows_a = p.taps == 3 ? 136 : 128;
   constexpr int NCH = BN / 32;             // epilogue chunks per tile
@@ -118,15 +80,16 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmA1);
     tma_prefetch_desc(&p.tmW);
-    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&op_full[s], 128); }
+    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&op_full[s], 8); }   // op_full: 4 warps x 2 CTAs
     for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 16); }    // acc_empty: 8 warps x 2 CTAs
     for (int s = 0; s < NR; ++s) { mbar_init(&rc_full[s], 1); mbar_init(&rc_empty[s], 4); }
     fence_barrier_init();
   }
-  if (warp == 3) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
+  if (warp == 3) { tmem_alloc_pair(tmem_slot, 2 * BN); tmem_relinquish_pair(); }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) SK_STAMP(7, 0);
@@ -137,9 +100,9 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       uint32_t ia = 0, ib = 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int n0 = (t % p.n_tiles) * BN;
-        const int mi = t / p.n_tiles;
-        const int b = mi / p.tiles_per_clip;
-        const int l0 = (mi % p.tiles_per_clip) * 128;
+        const int mi = t / p.n_tiles;                      // pair index: 256 rows of one clip
+        const int b = mi / pairs_per_clip;
+        const int l0 = (mi % pairs_per_clip) * 256 + (int)rank * 128;
         const int wcopy = b % p.w_bmod;
         for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
           const bool second = kc >= p.k1_chunks;
@@ -157,17 +120,18 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           for (int tap = 0; tap < ntap; ++tap, ++ib) {
             const int sb = ib % NB;
             mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
-            mbar_expect_tx(&b_full[sb], C::B_BYTES);
-            tma_load_3d(sB + sb * C::B_BYTES, &p.tmW, &b_full[sb], second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64, tap * p.N + n0, wcopy);
+            if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * C::B_BYTES);      // both halves complete on the leader's barrier
+            tma_load_3d_pair(sB + sb * C::B_BYTES, &p.tmW, mapa_u32(smem_u32(&b_full[sb]), 0), second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64,
+                             tap * p.N + n0 + (int)rank * (BN / 2), wcopy);
             SK_STAMP(1, ib);
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------- MMA issuer (leader CTA, M = 256 over the pair)
+      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 256, BN, 0, 0);
       uint32_t ia = 0, ib = 0, i = 0;
       for (int t = t_begin; t < t_end; ++t, ++i) {
         const uint32_t acc = i & 1;
@@ -178,8 +142,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
           const bool second = kc >= p.k1_chunks;
           const int sa = ia % NA;
-          mbar_wait(&a_full[sa], (ia / NA) & 1);
-          if (p.xf) mbar_wait(&op_full[sa], (ia / NA) & 1);
+          mbar_wait(&op_full[sa], (ia / NA) & 1);       // A tiles of both CTAs landed (and transformed)
           tc_fence_after();
           const uint32_t abase = smem_u32(sA + sa * C::A_BYTES);
           SK_STAMP(3, ia);
@@ -191,15 +154,15 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
             const uint32_t bbase = smem_u32(sB + sb * C::B_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_ss<false>(tacc, make_smem_desc_sw128(abase + tap * 128 + k * 32, 16, 1024),
-                             make_smem_desc_sw128(bbase + k * 32, 16, 1024), idesc, first ? 0u : 1u);
+              umma_ss_pair(tacc, make_smem_desc_sw128(abase + tap * 128 + k * 32, 16, 1024),
+                           make_smem_desc_sw128(bbase + k * 32, 16, 1024), idesc, first ? 0u : 1u);
               first = false;
             }
-            umma_commit(&b_empty[sb]);
+            umma_commit_pair(&b_empty[sb]);
           }
-          umma_commit(&a_empty[sa]);
+          umma_commit_pair(&a_empty[sa]);
         }
-        umma_commit(&acc_full[acc]);
+        umma_commit_pair(&acc_full[acc]);
       }
     }
   } else if (warp == 2) {
@@ -208,9 +171,9 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       uint32_t q = 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int n0 = (t % p.n_tiles) * BN;
-        const int mi = t / p.n_tiles;
-        const int b = mi / p.tiles_per_clip;
-        const int l0 = (mi % p.tiles_per_clip) * 128;
+        const int mi = t / p.n_tiles;                      // pair index: 256 rows of one clip
+        const int b = mi / pairs_per_clip;
+        const int l0 = (mi % pairs_per_clip) * 256 + (int)rank * 128;
         for (int c = 0; c < NCH; ++c, ++q) {
           const int rs = q % NR;
           mbar_wait(&rc_empty[rs], ((q / NR) & 1) ^ 1);
@@ -220,7 +183,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    if (p.xf) {
+    {
       // ------------------------------------------------------------- A transform (in place on the landed bf16 tile)
       const int tid = threadIdx.x - 128;        // 0..127
       const int g = tid & 7;                     // 16-byte chunk (8 channels) of the 128-byte row
@@ -228,9 +191,9 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       int cur_b = -1, cur_mi = -1;
       uint32_t ia = 0;
       for (int t = t_begin; t < t_end; ++t) {
-        const int mi = t / p.n_tiles;
-        const int b = mi / p.tiles_per_clip;
-        const int l0 = (mi % p.tiles_per_clip) * 128;
+        const int mi = t / p.n_tiles;                      // pair index: 256 rows of one clip
+        const int b = mi / pairs_per_clip;
+        const int l0 = (mi % pairs_per_clip) * 256 + (int)rank * 128;
         if (b != cur_b) {         // per-clip channel coefficients: y = x * a[c] + b[c]
           cur_b = b;
           named_bar(3, 128);
@@ -291,7 +254,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           const int sa = ia % NA;
           mbar_wait(&a_full[sa], (ia / NA) & 1);
           if (tid == 0) SK_STAMP(2, 2 * ia);
-          if (p.xf == 3 ? kc >= p.k1_chunks : kc < p.k1_chunks) {
+          if (p.xf != 0 && (p.xf == 3 ? kc >= p.k1_chunks : kc < p.k1_chunks)) {
             uint8_t* tile = sA + sa * C::A_BYTES;
             float ca[8], cb[8];
             uint32_t pa[4], pbh[4], pbl[4];
@@ -378,9 +341,10 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
               const int r = rsub + 16 * it;
               if (r < rows_a) *reinterpret_cast<uint4*>(tile + r * 128 + ((g ^ (r & 7)) << 4)) = u[it];
             }
-            fence_proxy_async();
+            fence_proxy_async_all();
           }
-          mbar_arrive(&op_full[sa]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&op_full[sa]), 0));
           if (tid == 0) SK_STAMP(2, 2 * ia + 1);
         }
       }
@@ -431,8 +395,8 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       const int n_idx = t % p.n_tiles;
       const int n0 = n_idx * BN;
       const int mi = t / p.n_tiles;
-      const int b = mi / p.tiles_per_clip;
-      const int l0 = (mi % p.tiles_per_clip) * 128;
+      const int b = mi / pairs_per_clip;
+      const int l0 = (mi % pairs_per_clip) * 256 + (int)rank * 128;
       const bool row_valid = l0 + row < p.L;
       const uint32_t acc = i & 1;
       if (b != cur_b || n_idx != cur_n) {
@@ -494,7 +458,8 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         tmem_ld_wait();
         if (c + 2 >= NCH) {           // this thread's last TMEM read of the tile: hand the accumulator back
           tc_fence_before();
-          mbar_arrive(&acc_empty[acc]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[acc]), 0));
         }
         if (et == 0) SK_STAMP(4, 4 * (qg >> 1) + 1);
         const int c0 = c * 32;
@@ -585,30 +550,25 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 3) tmem_dealloc(tmem_base, 2 * BN);
+  cluster_sync_all();            // the peer may still be reading this CTA's shared memory / arriving on its barriers
+  if (warp == 3) tmem_dealloc_pair(tmem_base, 2 * BN);
 }
 
 // ------------------------------------------------------------------------------------------------ instantiation table
-#define SFB_SK_LIST(X) X(128, 4) X(128, 8) X(128, 16) X(256, 8) X(256, 16) X(256, 32) X(256, 64) X(256, 128)
-
-inline int sk_find(int BN, int GS) {
-  int i = 0;
-#define X(a, b) if (BN == a && GS == b) return i; ++i;
-  SFB_SK_LIST(X)
-#undef X
-  return -1;
-}
-inline cudaError_t sk_set_attrs() {
+inline cudaError_t sk2_set_attrs() {
   cudaError_t e = cudaSuccess;
-#define X(a, b) if (e == cudaSuccess) e = cudaFuncSetAttribute(sk_kernel<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<a>::SMEM);
+#define X(a, b) if (e == cudaSuccess) e = cudaFuncSetAttribute(sk2_kernel<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<a>::SMEM);
   SFB_SK_LIST(X)
 #undef X
   return e;
 }
-inline void sk_launch(int id, const SkParams& p, int num_sms, cudaStream_t st) {
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+// grid = 2 x min(pair tiles, SM pairs); ids are those of sk_find()
+inline void sk2_launch(int id, const SkParams& p, int num_sms, cudaStream_t st) {
+  const int pairs_per_clip = (p.tiles_per_clip + 1) / 2;
+  const int total_pt = (p.total_tiles / (p.tiles_per_clip * p.n_tiles)) * pairs_per_clip * p.n_tiles;
+  const int npairs = total_pt < num_sms / 2 ? total_pt : num_sms / 2;
   int i = 0;
-#define X(a, b) if (id == i++) { sk_kernel<a, b><<<grid, 512, SkCfg<a>::SMEM, st>>>(p); return; }
+#define X(a, b) if (id == i++) { sk2_kernel<a, b><<<2 * npairs, 512, Sk2Cfg<a>::SMEM, st>>>(p); return; }
   SFB_SK_LIST(X)
 #undef X
 }
