@@ -22,7 +22,9 @@
 #include "prepare.cuh"
 #include "rk_tc.cuh"
 #include "sk_tc.cuh"
+#ifdef SFB_ENABLE_SK2   // experimental CTA-pair variant (slower than the single-CTA kernel as of r1; not built by default)
 #include "sk2_tc.cuh"
+#endif
 
 using namespace sfb;
 
@@ -255,7 +257,11 @@ struct Engine : EngineBase {
   int F_total = 0, XB_total = 0, n_gn = 0;
   bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aids: force the unfused generic path
   bool no_sk = getenv("SFB_NO_SK") != nullptr;
+#ifdef SFB_ENABLE_SK2
   bool no_sk2 = getenv("SFB_SK2") == nullptr;     // SFB_SK2=1: CTA-pair streaming-K kernel (sk2_tc.cuh) instead of the single-CTA one
+#else
+  bool no_sk2 = true;
+#endif
 
   struct Op {
     int kind = 0, depth = 0, stack = 0, item = 0;
@@ -372,7 +378,9 @@ struct Engine : EngineBase {
     if (set_kernel_attrs<T>() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (kBF16 && rk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (rk) failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (kBF16 && sk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (sk) failed: %s", cudaGetErrorString(cudaGetLastError()));
+#ifdef SFB_ENABLE_SK2
     if (kBF16 && sk2_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (sk2) failed: %s", cudaGetErrorString(cudaGetLastError()));
+#endif
 
     // time conditioning (A.3)
     t_w = upload_f(get("time.weights", {128}));
@@ -1322,8 +1330,11 @@ struct Engine : EngineBase {
               if (o.sk_ft_is_mod) { p.mod = sc.frow + o.ft_off; p.mod_bstride = sc.bstride; p.mod_bmod = sc.bmod; p.w_bmod = sc.bmod; }
               else { p.colscale = sc.frow + o.ft_off; p.cs_bstride = sc.bstride; p.cs_bmod = sc.bmod; }
             }
-            if (no_sk2) sk_launch(o.sk_id, p, num_sms(), st);
-            else sk2_launch(o.sk_id, p, num_sms(), st);
+            const int epi = sk_epi_of(p.ln_fold, p.resid_mode, p.colscale != nullptr);
+#ifdef SFB_ENABLE_SK2
+            if (!no_sk2) { sk2_launch(o.sk_id, p, num_sms(), st); break; }
+#endif
+            sk_launch(o.sk_id, epi, p, num_sms(), st);
           }
           break;
         }

@@ -83,7 +83,15 @@ template <int BN> struct SkCfg {
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int BN, int GS>
+// EPI: compile-time epilogue shape (the per-column math sits in the hottest loop of the small-K ops, where uniform
+// run-time branches cost a third of the issue slots and pin every shared-memory load behind a branch):
+//   0 plain   1 + resid   2 LayerNorm fold   3 LayerNorm fold + Modulation(resid)   4 colscale + resid   5 run-time flags
+__host__ __device__ constexpr int sk_epi_of(int ln_fold, int resid_mode, int has_colscale) {
+  return (!ln_fold && resid_mode == 0 && !has_colscale) ? 0 : (!ln_fold && resid_mode == 1 && !has_colscale) ? 1
+       : (ln_fold && resid_mode == 0 && !has_colscale) ? 2 : (ln_fold && resid_mode == 2 && !has_colscale) ? 3
+       : (!ln_fold && resid_mode == 1 && has_colscale) ? 4 : 5;
+}
+template <int BN, int GS, int EPI>
 __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkParams p) {
   using C = SkCfg<BN>;
   constexpr int NA = C::NA, NB = C::NB, NR = C::NR, NT = C::NT;
@@ -397,7 +405,9 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
     const int row = q4 * 32 + lane;
     const int et = threadIdx.x - 256;          // 0..255
     const uint32_t lane_off = uint32_t(q4 * 32) << 16;
-    const int resid_mode = p.resid_mode;
+    const int resid_mode = EPI == 5 ? p.resid_mode : (EPI == 1 || EPI == 4) ? 1 : EPI == 3 ? 2 : 0;
+    const bool ln_fold = EPI == 5 ? p.ln_fold != 0 : (EPI == 2 || EPI == 3);
+    const bool use_mul = EPI == 5 || EPI == 4;
     const bool has_out_r = p.has_out_r != 0, has_out_t = p.has_out_t != 0;
     float* ep_mul = sVEC;             // [BN] colscale
     float* ep_add = sVEC + BN;        // [BN] bias * colscale + rowvec
@@ -448,8 +458,8 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           const size_t wrow = (size_t)(b % p.w_bmod) * p.ws_bstride + n0 + n;
           ep_mul[n] = cs;
           ep_add[n] = ((p.bias ? p.bias[nm] : 0.f) + (p.addvec ? p.addvec[wrow] : 0.f)) * cs + rv;
-          if (p.ln_fold) ep_ws[n] = p.ws[wrow];
-          if (p.resid_mode == 2) {
+          if (ln_fold) ep_ws[n] = p.ws[wrow];
+          if (resid_mode == 2) {
             const float* md = p.mod + (size_t)(b % p.mod_bmod) * p.mod_bstride;
             ep_g[n] = 1.f + md[n0 + n];
             ep_sh[n] = md[p.N + n0 + n];
@@ -458,14 +468,13 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         named_bar(2, 256);
       }
       float r_mean = 0.f, r_rstd = 0.f;
-      if ((p.resid_mode == 2 || p.ln_fold) && row_valid) {     // LayerNorm statistics of this thread's A1 / residual row
+      if ((resid_mode == 2 || ln_fold) && row_valid) {     // LayerNorm statistics of this thread's A1 / residual row
         const float* rsrc = p.rowstats_in + ((size_t)b * p.L + l0 + row) * p.rs_parts * 2;
         float a = 0.f, c = 0.f;
         for (int j = 0; j < p.rs_parts; ++j) { a += rsrc[2 * j]; c += rsrc[2 * j + 1]; }
         r_mean = a / (float)p.K1;
         r_rstd = rsqrtf(fmaxf(c / (float)p.K1 - r_mean * r_mean, 0.f) + p.eps);
       }
-      const bool ln_fold = p.ln_fold != 0;
       const float f_mul = ln_fold ? r_rstd : 1.f, f_sub = ln_fold ? -r_rstd * r_mean : 0.f;
       if (et == 0) SK_STAMP(6, 2 * i);
       mbar_wait(&acc_full[acc], (i >> 1) & 1);
@@ -501,7 +510,8 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         float y[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 mu = *reinterpret_cast<const float4*>(&ep_mul[c0 + j4 * 4]);
+          float4 mu = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (use_mul) mu = *reinterpret_cast<const float4*>(&ep_mul[c0 + j4 * 4]);
           const float4 ad = *reinterpret_cast<const float4*>(&ep_add[c0 + j4 * 4]);
           uint8_t* slot = rt + row * 128 + ((j4 ^ sw7) << 4);
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -514,15 +524,23 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           }
           float d0 = __uint_as_float(v[j4 * 4 + 0]), d1 = __uint_as_float(v[j4 * 4 + 1]);
           float d2 = __uint_as_float(v[j4 * 4 + 2]), d3 = __uint_as_float(v[j4 * 4 + 3]);
-          if (ln_fold) {            // D' = rstd (D - mean ws[n])
+          if (ln_fold && !use_mul) {   // D' + add = rstd D + (-rstd mean ws[n] + add[n])   (two FMAs per value)
             const float4 wsv = *reinterpret_cast<const float4*>(&ep_ws[c0 + j4 * 4]);
-            d0 = fmaf(f_mul, d0, f_sub * wsv.x); d1 = fmaf(f_mul, d1, f_sub * wsv.y);
-            d2 = fmaf(f_mul, d2, f_sub * wsv.z); d3 = fmaf(f_mul, d3, f_sub * wsv.w);
+            y[j4 * 4 + 0] = fmaf(f_mul, d0, fmaf(f_sub, wsv.x, ad.x)) + x.x;
+            y[j4 * 4 + 1] = fmaf(f_mul, d1, fmaf(f_sub, wsv.y, ad.y)) + x.y;
+            y[j4 * 4 + 2] = fmaf(f_mul, d2, fmaf(f_sub, wsv.z, ad.z)) + x.z;
+            y[j4 * 4 + 3] = fmaf(f_mul, d3, fmaf(f_sub, wsv.w, ad.w)) + x.w;
+          } else {
+            if (ln_fold) {            // D' = rstd (D - mean ws[n])
+              const float4 wsv = *reinterpret_cast<const float4*>(&ep_ws[c0 + j4 * 4]);
+              d0 = fmaf(f_mul, d0, f_sub * wsv.x); d1 = fmaf(f_mul, d1, f_sub * wsv.y);
+              d2 = fmaf(f_mul, d2, f_sub * wsv.z); d3 = fmaf(f_mul, d3, f_sub * wsv.w);
+            }
+            y[j4 * 4 + 0] = fmaf(d0, mu.x, ad.x) + x.x;
+            y[j4 * 4 + 1] = fmaf(d1, mu.y, ad.y) + x.y;
+            y[j4 * 4 + 2] = fmaf(d2, mu.z, ad.z) + x.z;
+            y[j4 * 4 + 3] = fmaf(d3, mu.w, ad.w) + x.w;
           }
-          y[j4 * 4 + 0] = fmaf(d0, mu.x, ad.x) + x.x;
-          y[j4 * 4 + 1] = fmaf(d1, mu.y, ad.y) + x.y;
-          y[j4 * 4 + 2] = fmaf(d2, mu.z, ad.z) + x.z;
-          y[j4 * 4 + 3] = fmaf(d3, mu.w, ad.w) + x.w;
           if (has_out_r) *reinterpret_cast<float4*>(slot) = make_float4(y[j4 * 4], y[j4 * 4 + 1], y[j4 * 4 + 2], y[j4 * 4 + 3]);
         }
         if (has_out_t) {
@@ -600,17 +618,21 @@ inline int sk_find(int BN, int GS) {
 }
 inline cudaError_t sk_set_attrs() {
   cudaError_t e = cudaSuccess;
-#define X(a, b) if (e == cudaSuccess) e = cudaFuncSetAttribute(sk_kernel<a, b>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<a>::SMEM);
+#define Y(a, b, c) if (e == cudaSuccess) e = cudaFuncSetAttribute(sk_kernel<a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<a>::SMEM);
+#define X(a, b) Y(a, b, 0) Y(a, b, 1) Y(a, b, 2) Y(a, b, 3) Y(a, b, 4) Y(a, b, 5)
   SFB_SK_LIST(X)
 #undef X
+#undef Y
   return e;
 }
-inline void sk_launch(int id, const SkParams& p, int num_sms, cudaStream_t st) {
+inline void sk_launch(int id, int epi, const SkParams& p, int num_sms, cudaStream_t st) {
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   int i = 0;
-#define X(a, b) if (id == i++) { sk_kernel<a, b><<<grid, 512, SkCfg<a>::SMEM, st>>>(p); return; }
+#define Y(a, b, c) if (epi == c) { sk_kernel<a, b, c><<<grid, 512, SkCfg<a>::SMEM, st>>>(p); return; }
+#define X(a, b) if (id == i++) { Y(a, b, 0) Y(a, b, 1) Y(a, b, 2) Y(a, b, 3) Y(a, b, 4) Y(a, b, 5) }
   SFB_SK_LIST(X)
 #undef X
+#undef Y
 }
 
 }  // namespace sfb
