@@ -45,6 +45,7 @@ __host__ __device__ constexpr int attn_smem_bytes() {
 
 template <typename T>
 __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_constant__ AttnParams<T> p) {
+  pdl_trigger();
   using TR = ElemTraits<T>;
   constexpr int AE = TR::kAtomElems;            // elements per 128-byte row
   constexpr int DA = kHeadDim / AE;             // atoms along head dim (1 bf16, 2 tf32)
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
   if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  pdl_wait();            // everything above is independent of the previous kernel's output
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + BKV;

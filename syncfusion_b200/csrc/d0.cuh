@@ -44,6 +44,8 @@ __device__ __forceinline__ void stats8_block_reduce(const float* y, bool valid, 
 __global__ void __launch_bounds__(256) d0_down_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y,
                                                       double* __restrict__ stats, int L, int Bx) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ Stats8Smem s_st;
   const int b = blockIdx.y;
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,6 +66,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv3_c8_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* resid, float* out_r,
                                                        T* __restrict__ out_t, double* __restrict__ stats, int L) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_w[24 * 8];
   __shared__ Stats8Smem s_st;
   if (threadIdx.x < 192) s_w[threadIdx.x] = w[threadIdx.x];
@@ -110,6 +114,8 @@ __global__ void __launch_bounds__(256) inject_c8_kernel(const T* __restrict__ m_
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         const float* __restrict__ xbias, float* out_r, T* __restrict__ out_t,
                                                         double* __restrict__ stats, int L, int Bc, int xb_stride) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_w[(8 + CTX) * 8];
   __shared__ Stats8Smem s_st;
   for (int i = threadIdx.x; i < (8 + CTX) * 8; i += blockDim.x) s_w[i] = w[i];
@@ -148,6 +154,8 @@ __global__ void __launch_bounds__(256) d0_up_kernel(const T* __restrict__ c, con
                                                     const float* __restrict__ skip_scale, int sstride, int smod,
                                                     const float* __restrict__ x, float* __restrict__ v, int L, int Bx,
                                                     int taps) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= L) return;

@@ -63,6 +63,8 @@ template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(256) gn_apply_silu_kernel(const Tin* __restrict__ in, const double* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             Tout* __restrict__ out, int L, int C, int gs, float eps) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_ab[];
   __shared__ float s_g[16];   // per group: mean, rstd
   const int b = blockIdx.y;
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* in, const floa
                                                      const float* __restrict__ shift, int bstride, int bmod,
                                                      Tout* __restrict__ out_t, float* out_r, size_t rows, int rows_per_clip,
                                                      int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int lpr = (C / 8 < 32) ? C / 8 : 32;
   const int rpw = 32 / lpr;
   const int lane = threadIdx.x & 31;
@@ -171,6 +175,8 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(const float* __rest
                                                              float* __restrict__ x_out, float* __restrict__ traj_x,
                                                              float* __restrict__ traj_v, size_t n, int cfg, float scale,
                                                              float a, float b, float a2, float b2) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   const float4 xv = *reinterpret_cast<const float4*>(x_eval + i);

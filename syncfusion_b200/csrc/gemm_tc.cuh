@@ -76,6 +76,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <typename T, int BN>
 __global__ void __launch_bounds__(kGemmThreads, GemmCfg<BN>::kCtasPerSm) gemm_tc_kernel(const __grid_constant__ GemmParams<T> p) {
+  pdl_trigger();
   using TR = ElemTraits<T>;
   constexpr int BK = TR::kAtomElems;
   constexpr int S = GemmCfg<BN>::kStages;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(kGemmThreads, GemmCfg<BN>::kCtasPerSm) gemm_tc
   if (warp == 1) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  pdl_wait();            // everything above is independent of the previous kernel's output
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

@@ -102,6 +102,8 @@ struct FoldItem {
 };
 __global__ void __launch_bounds__(256) inject_fold_kernel(const FoldItem* __restrict__ items, int n_items, int total_rows,
                                                           const float* __restrict__ frow, int bstride, int copies) {
+  pdl_trigger();
+  pdl_wait();
   const int gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= total_rows * copies) return;

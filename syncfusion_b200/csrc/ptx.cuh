@@ -2,6 +2,7 @@
 // Hand-written; descriptor bit layouts follow the PTX ISA "tcgen05 matrix/instruction descriptor" tables.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -60,6 +61,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) { __trap(); }
   }
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel of the per-step chain calls pdl_trigger() first (the NEXT kernel's CTAs may be scheduled as soon as
+// SMs free up and run their prologue) and pdl_wait() before touching global memory (blocks until the PREVIOUS kernel
+// has completed and flushed).  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void prefetch_l1(const void* g) { asm volatile("prefetch.global.L1 [%0];" ::"l"(g)); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("SFB_NO_PDL") ? 0 : 1;
+  return on != 0;
+}
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute.
+// ONLY for kernels that call pdl_wait() before their first dependent global access.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 // ------------------------------------------------------------------ TMA

@@ -161,6 +161,7 @@ struct RkCfg {
 
 template <int K1, int N, int TAPS, int XF, int EPI, int BMOD, int USE_R>
 __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThreads, 1) rk_kernel(const __grid_constant__ RkParams p) {
+  pdl_trigger();
   using C = RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>;
   constexpr int NSR = C::NSR;
   extern __shared__ uint8_t smem_raw[];
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
   if (warp == 1) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  pdl_wait();            // everything above is independent of the previous kernel's output
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -652,7 +654,7 @@ inline void rk_launch(int id, const RkParams& p, int num_sms, cudaStream_t st) {
   int i = 0;
 #define X(a, b, c, d, e_, f, g)                                                                                          \
   if (id == i++) {                                                                                                       \
-    rk_kernel<a, b, c, d, e_, f, g><<<grid, RkCfg<a, b, c, d, e_, f, g>::kThreads, RkCfg<a, b, c, d, e_, f, g>::SMEM, st>>>(p); \
+    launch_pdl(rk_kernel<a, b, c, d, e_, f, g>, grid, RkCfg<a, b, c, d, e_, f, g>::kThreads, RkCfg<a, b, c, d, e_, f, g>::SMEM, st, p); \
     return;                                                                                                              \
   }
   SFB_RK_LIST(X)

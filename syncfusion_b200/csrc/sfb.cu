@@ -191,7 +191,7 @@ void launch_gemm_bn(GemmParams<T> p, int B, cudaStream_t st) {
   p.n_tiles = p.N / BN;
   p.total_tiles = B * p.tiles_per_clip * p.n_tiles;
   const int grid = std::min(p.total_tiles, num_sms() * GemmCfg<BN>::kCtasPerSm);   // persistent CTAs
-  gemm_tc_kernel<T, BN><<<grid, kGemmThreads, gemm_smem_bytes<T, BN>(), st>>>(p);
+  launch_pdl(gemm_tc_kernel<T, BN>, grid, kGemmThreads, gemm_smem_bytes<T, BN>(), st, p);
 }
 template <typename T>
 void launch_gemm(const GemmParams<T>& p, int BN, int B, cudaStream_t st) {
@@ -1246,7 +1246,7 @@ struct Engine : EngineBase {
     const unsigned blocks = (unsigned)((warps + 7) / 8);
     const float* scale = o.ft_off >= 0 ? sc.frow + o.ft_off : nullptr;
     const float* shift = o.ft_off >= 0 ? sc.frow + o.ft_off + o.C : nullptr;
-    ln_mod_kernel<T, NV><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(o.in), scale, shift, sc.bstride, sc.bmod,
+    launch_pdl(ln_mod_kernel<T, NV>, blocks, 256, 0, st, reinterpret_cast<const float*>(o.in), scale, shift, sc.bstride, sc.bmod,
                                                 reinterpret_cast<T*>(o.out_t), o.out_r, rows, o.L, o.C, 1e-5f);
   }
 
@@ -1256,7 +1256,7 @@ struct Engine : EngineBase {
     ++launches;
     if (!fold_items.empty()) {     // per-evaluation scaled inject weights (LayerNorm fold): one warp per (copy, row)
       const size_t warps = (size_t)fold_rows * sc.bmod;
-      inject_fold_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(fold_items_dev, (int)fold_items.size(), fold_rows, sc.frow,
+      launch_pdl(inject_fold_kernel, (unsigned)((warps + 7) / 8), 256, 0, st, fold_items_dev, (int)fold_items.size(), fold_rows, sc.frow,
                                                                      sc.bstride, sc.bmod);
       ++launches;
     }
@@ -1273,31 +1273,31 @@ struct Engine : EngineBase {
       if (profiling) cudaEventRecord(prof_ev[2 * i], st);
       switch (o.kind) {
         case OP_D0_DOWN:
-          d0_down_kernel<<<dim3(lb, o.B), 256, 0, st>>>(sc.x, o.w0, o.w1, o.out_r, o.stats_out, o.L, Bx);
+          launch_pdl(d0_down_kernel, dim3(lb, o.B), 256, 0, st, sc.x, o.w0, o.w1, o.out_r, o.stats_out, o.L, Bx);
           break;
         case OP_GN: {
           const size_t nvec = (size_t)o.L * o.C / 8;
           unsigned bpc = (unsigned)std::min<size_t>(std::max<size_t>((nvec + 1023) / 1024, 1), 8192);
           const size_t sm = (size_t)2 * o.C * sizeof(float);
           if (o.in_is_f32)
-            gn_apply_silu_kernel<float, T><<<dim3(bpc, o.B), 256, sm, st>>>(reinterpret_cast<const float*>(o.in), o.stats_in, o.w0, o.w1,
+            launch_pdl(gn_apply_silu_kernel<float, T>, dim3(bpc, o.B), 256, sm, st, reinterpret_cast<const float*>(o.in), o.stats_in, o.w0, o.w1,
                                                                           reinterpret_cast<T*>(o.out_t), o.L, o.C, o.gs, 1e-5f);
           else
-            gn_apply_silu_kernel<T, T><<<dim3(bpc, o.B), 256, sm, st>>>(reinterpret_cast<const T*>(o.in), o.stats_in, o.w0, o.w1,
+            launch_pdl(gn_apply_silu_kernel<T, T>, dim3(bpc, o.B), 256, sm, st, reinterpret_cast<const T*>(o.in), o.stats_in, o.w0, o.w1,
                                                                       reinterpret_cast<T*>(o.out_t), o.L, o.C, o.gs, 1e-5f);
           break;
         }
         case OP_CONV_C8:
-          conv3_c8_kernel<T><<<dim3(lb, o.B), 256, 0, st>>>(reinterpret_cast<const T*>(o.in), o.w0, o.w1, o.resid, o.out_r,
+          launch_pdl(conv3_c8_kernel<T>, dim3(lb, o.B), 256, 0, st, reinterpret_cast<const T*>(o.in), o.w0, o.w1, o.resid, o.out_r,
                                                             reinterpret_cast<T*>(o.out_t), o.stats_out, o.L);
           break;
         case OP_INJ_C8:
-          inject_c8_kernel<T, 2><<<dim3(lb, o.B), 256, 0, st>>>(reinterpret_cast<const T*>(o.in), o.resid,
+          launch_pdl(inject_c8_kernel<T, 2>, dim3(lb, o.B), 256, 0, st, reinterpret_cast<const T*>(o.in), o.resid,
                                                                reinterpret_cast<const T*>(o.in2), o.w0, o.w1, o.w2, o.out_r,
                                                                reinterpret_cast<T*>(o.out_t), o.stats_out, o.L, Bx, XB_total);
           break;
         case OP_D0_UP:
-          d0_up_kernel<T><<<dim3(lb, o.B), 256, 0, st>>>(reinterpret_cast<const T*>(o.in), o.w0, o.fscalar, sc.frow + o.ft_off,
+          launch_pdl(d0_up_kernel<T>, dim3(lb, o.B), 256, 0, st, reinterpret_cast<const T*>(o.in), o.w0, o.fscalar, sc.frow + o.ft_off,
                                                         sc.bstride, sc.bmod, sc.x, o.out_r, o.L, Bx, o.taps);
           break;
         case OP_GEMM: {
@@ -1348,7 +1348,7 @@ struct Engine : EngineBase {
         }
         case OP_ATTN: {
           dim3 grid((o.L + 127) / 128, 8, o.B);
-          attn_tc_kernel<T><<<grid, kAttnThreads, attn_smem_bytes<T>(), st>>>(o.ap);
+          launch_pdl(attn_tc_kernel<T>, grid, kAttnThreads, attn_smem_bytes<T>(), st, o.ap);
           break;
         }
       }
@@ -1456,7 +1456,7 @@ struct Engine : EngineBase {
       rc = run_unet(sc, st);
       if (rc) return rc;
       const float a = cosf(sig[i] * hp), b = sinf(sig[i] * hp), a2 = cosf(sig[i + 1] * hp), b2 = sinf(sig[i + 1] * hp);
-      sampler_update_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(
+      launch_pdl(sampler_update_kernel, (unsigned)((n / 4 + 255) / 256), 256, 0, st, 
           xe, at<float>(plan.lay.veff), xs, traj_x ? traj_x + (size_t)i * n : nullptr, traj_v ? traj_v + (size_t)i * n : nullptr,
           n, cfg_on, scale, a, b, a2, b2);
       ++launches;

@@ -93,6 +93,7 @@ __host__ __device__ constexpr int sk_epi_of(int ln_fold, int resid_mode, int has
 }
 template <int BN, int GS, int EPI>
 __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkParams p) {
+  pdl_trigger();
   using C = SkCfg<BN>;
   constexpr int NA = C::NA, NB = C::NB, NR = C::NR, NT = C::NT;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
   if (warp == 3) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  pdl_wait();            // everything above is independent of the previous kernel's output
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) SK_STAMP(7, 0);
@@ -445,6 +447,25 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       const int l0 = (mi % p.tiles_per_clip) * 128;
       const bool row_valid = l0 + row < p.L;
       const uint32_t acc = i & 1;
+      if (t + 1 < t_end) {       // warm L1 with the NEXT tile's per-column vectors and per-row statistics (global latency off the path)
+        const int n_idx2 = (t + 1) % p.n_tiles, mi2 = (t + 1) / p.n_tiles;
+        const int b2 = mi2 / p.tiles_per_clip, l02 = (mi2 % p.tiles_per_clip) * 128, n02 = n_idx2 * BN;
+        if ((resid_mode == 2 || ln_fold) && l02 + row < p.L) prefetch_l1(p.rowstats_in + ((size_t)b2 * p.L + l02 + row) * p.rs_parts * 2);
+        if (et < BN && (b2 != b || n_idx2 != n_idx)) {
+          const int nm2 = (n02 + et) % p.bias_mod;
+          const size_t wrow2 = (size_t)(b2 % p.w_bmod) * p.ws_bstride + n02 + et;
+          if (p.bias) prefetch_l1(&p.bias[nm2]);
+          if (use_mul && p.colscale) prefetch_l1(&p.colscale[(size_t)(b2 % p.cs_bmod) * p.cs_bstride + nm2]);
+          if (p.rowvec) prefetch_l1(&p.rowvec[(size_t)b2 * p.rowvec_stride + nm2]);
+          if (p.addvec) prefetch_l1(&p.addvec[wrow2]);
+          if (ln_fold) prefetch_l1(&p.ws[wrow2]);
+          if (resid_mode == 2) {
+            const float* md2 = p.mod + (size_t)(b2 % p.mod_bmod) * p.mod_bstride;
+            prefetch_l1(&md2[n02 + et]);
+            prefetch_l1(&md2[p.N + n02 + et]);
+          }
+        }
+      }
       if (b != cur_b || n_idx != cur_n) {
         const int goff = (n0 / GS) & 7;
         if (b != cur_b || goff != cur_goff) flush_stats(cur_b, cur_goff);
@@ -628,7 +649,7 @@ inline cudaError_t sk_set_attrs() {
 inline void sk_launch(int id, int epi, const SkParams& p, int num_sms, cudaStream_t st) {
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   int i = 0;
-#define Y(a, b, c) if (epi == c) { sk_kernel<a, b, c><<<grid, 512, SkCfg<a>::SMEM, st>>>(p); return; }
+#define Y(a, b, c) if (epi == c) { launch_pdl(sk_kernel<a, b, c>, grid, 512, SkCfg<a>::SMEM, st, p); return; }
 #define X(a, b) if (id == i++) { Y(a, b, 0) Y(a, b, 1) Y(a, b, 2) Y(a, b, 3) Y(a, b, 4) Y(a, b, 5) }
   SFB_SK_LIST(X)
 #undef X
