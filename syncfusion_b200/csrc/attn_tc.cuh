@@ -2,12 +2,15 @@
 //   out[b, i, h, :] = softmax_j(q[b,i,h,:] . k[b,j,h,:] / sqrt(64)) v[b,j,h,:]     8 heads x 64, non-causal, no mask.
 // Input is the fused QKV projection output [B, N, 1536] (q | k | v, heads contiguous 64-wide), output [B, N, 512].
 //
-// One CTA = one 128-query tile of one (clip, head).  Warp 0 lane 0: TMA producer (Q once, K/V tiles double
-// buffered).  Warp 1 lane 0: tcgen05.mma issuer: S = Q K^T (K-major x K-major) into TMEM, then O_j = P V with V
-// consumed straight from its TMA tile as an MN-major B operand.  Warps 2-5 (128 threads, one query row each):
-// online softmax in fp32 - S is read from TMEM twice (row max, then exp2), P is written to 128B-swizzled smem in
-// operand precision, the per-tile P V product is read back from TMEM and folded into a register accumulator with
-// the running rescale.  The [B, 8, N, N] score matrix the reference materialises never exists.
+// One CTA = one 128-query tile of one (clip, head), two CTAs per SM.  Warp 0 lane 0: TMA producer (Q once, K/V tiles
+// double buffered).  Warp 1 lane 0: tcgen05.mma issuer: S = Q K^T (K-major x K-major) into TMEM, O += P V ACCUMULATED
+// IN TMEM over all key tiles (V consumed straight from its TMA tile as an MN-major B operand).  Warps 2-5 (128
+// threads, one query row each): S is read from TMEM ONCE into registers (which frees the S columns at once: the MMA
+// warp issues S(j+1) while softmax(j) is still computing), row max, exp2, P written to 128B-swizzled smem in operand
+// precision.  The running max is LAZY: the O accumulator and the row sum are rescaled only when a row's max grows by
+// more than 2^8 (then the warp reads O from TMEM, scales, writes it back); otherwise probabilities simply stay
+// relative to the older max (<= 2^8, exact in fp32 / harmless in bf16) - no per-tile O read-back, no per-tile
+// multiply of the accumulator.  The [B, 8, N, N] score matrix the reference materialises never exists.
 #pragma once
 #include "ptx.cuh"
 
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
   uint64_t* s_full = bars + 5;
   uint64_t* p_ready = bars + 6;
   uint64_t* o_full = bars + 7;
-  uint64_t* o_free = bars + 8;
+  uint64_t* s_free = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
     mbar_init(s_full, 1);
     mbar_init(p_ready, 128);
     mbar_init(o_full, 1);
-    mbar_init(o_free, 128);
+    mbar_init(s_free, 128);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
         umma_ss<TR::kTF32>(tmem_S, da, db, idesc_s, k != 0);
       }
     };
-    auto issue_o = [&](int s) {
+    auto issue_o = [&](int s, bool accumulate) {
       const uint32_t ap = smem_u32(sP), av = smem_u32(sKV + s * 2 * kKBytes + kKBytes);
 #pragma unroll
       for (int k = 0; k < BKV / UK; ++k) {
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
         // bf16: SWIZZLE_128B, 8-key groups; tf32: SWIZZLE_128B_BASE32B, 4-key groups 512 bytes apart.
         const uint64_t db = (sizeof(T) == 2) ? make_smem_desc(av + k * UK * 128, BKV * 128, 1024, 2)
                                              : make_smem_desc(av + k * UK * 128, BKV * 128, 512, 1);
-        umma_ss<TR::kTF32>(tmem_O, da, db, idesc_o, k != 0);
+        umma_ss<TR::kTF32>(tmem_O, da, db, idesc_o, (accumulate || k != 0) ? 1u : 0u);
       }
     };
     mbar_wait(q_full, 0);
@@ -144,135 +147,139 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
     umma_commit(s_full);
     for (int j = 0; j < nkv; ++j) {
       const int s = j & 1;
-      mbar_wait(p_ready, j & 1);
-      if (j > 0) mbar_wait(o_free, (j - 1) & 1);
-      tc_fence_after();
-      issue_o(s);
-      umma_commit(o_full);
-      umma_commit(&kv_empty[s]);
-      if (j + 1 < nkv) {
+      if (j + 1 < nkv) {            // S(j+1) as soon as the softmax warps hold S(j) in registers
         const int s2 = (j + 1) & 1;
+        mbar_wait(s_free, j & 1);
         mbar_wait(&kv_full[s2], ((j + 1) >> 1) & 1);
         tc_fence_after();
         issue_s(s2);
         umma_commit(s_full);
       }
+      mbar_wait(p_ready, j & 1);
+      tc_fence_after();
+      issue_o(s, j > 0);
+      umma_commit(o_full);
+      umma_commit(&kv_empty[s]);
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------- softmax + output (one query row per thread)
+    // ------------------------------------------------------------- softmax (one query row per thread)
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
-    float o_acc[kHeadDim];
-#pragma unroll
-    for (int i = 0; i < kHeadDim; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_used = -INFINITY, l_run = 0.f;
     const float sc = p.scale_log2;
     for (int j = 0; j < nkv; ++j) {
       const int kv_valid = min(BKV, p.n_tokens - j * BKV);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      float mx = m_run;
-      const bool full_tile = kv_valid == BKV;   // tile-uniform: only the last tile of a ragged sequence is masked
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c, v);
-        tmem_ld_wait();
-        if (full_tile) {
+      uint32_t v[BKV];
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-        } else {
+      for (int c = 0; c < BKV; c += 32) tmem_ld32(tmem_S + lane_off + c, v + c);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);                       // the S columns may be overwritten by S(j+1)
+      if (kv_valid != BKV) {                     // tile-uniform: only the last tile of a ragged sequence is masked
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i < kv_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < BKV; ++i)
+          if (i >= kv_valid) v[i] = 0xFF800000u;   // -inf
+      }
+      float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]);
+#pragma unroll
+      for (int i = 2; i < BKV; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1])); }
+      const float mx = fmaxf(mx0, mx1);
+      // lazy running max: rescale only when this row's max grew by more than 2^8 relative to the max in use
+      const bool need = (mx - m_used) * sc > 8.f;             // true on the first tile (m_used = -inf)
+      bool o_waited = false;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ((m_used == -INFINITY) ? 0.f : exp2f((m_used - mx) * sc)) : 1.f;
+        if (need) m_used = mx;
+        l_run *= alpha;
+        if (j > 0) {               // O(j-1) is complete: read - scale - write back (whole warp, per-lane factor)
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
+          o_waited = true;
+#pragma unroll
+          for (int c = 0; c < kHeadDim; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_off + c, o);
+          }
+          tmem_st_wait();
         }
       }
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - mx) * sc);
-      const float moff = mx * sc;
+      const float moff = m_used * sc;
       float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c, v);
-        tmem_ld_wait();
-        float pv[32];
-        if (full_tile) {
+      // probabilities in place (fp32), row sum on the un-rounded values (two independent chains); the operand-precision
+      // rounding of P is zero-mean, so the normaliser differs from sum(round(P)) by ~1e-4 relative at most.
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(v[i]), sc, -moff));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = (c + i < kv_valid) ? fast_exp2(fmaf(__uint_as_float(v[i]), sc, -moff)) : 0.f;
-        }
-        // row sum in fp32 on the un-rounded probabilities (two independent chains); the operand-precision rounding of
-        // P is zero-mean, so the normaliser differs from sum(round(P)) by ~1e-4 relative at most.
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) { rs0 += pv[i]; rs1 += pv[i + 1]; }
-        // write this row's 32 probabilities into the swizzled K-major P tile (operand precision)
+      for (int i = 0; i < BKV; i += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, -moff)), p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -moff));
+        rs0 += p0; rs1 += p1;
         if constexpr (sizeof(T) == 2) {
-          const int atom = c / AE;               // 64 keys per atom
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {       // 4 chunks of 8 keys (16 bytes)
-            const int cc = ((c % AE) / 8) + ch;  // chunk index inside the 128-byte row
-            uint32_t w[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[ch * 8 + 2 * t], pv[ch * 8 + 2 * t + 1]);
-              w[t] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(sP + atom * 128 * 128 + r * 128 + ((cc ^ (r & 7)) * 16));
-            *dst = make_uint4(w[0], w[1], w[2], w[3]);
-          }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+          v[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);       // packed pair i/2 (slots below i are already consumed)
         } else {
-          const int atom = c / AE;               // 32 keys per atom: this 32-column pass fills one atom row
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {       // 8 chunks of 4 keys
-            uint4* dst = reinterpret_cast<uint4*>(sP + atom * 128 * 128 + r * 128 + ((ch ^ (r & 7)) * 16));
-            *dst = make_uint4(__float_as_uint(from_f32<float>(pv[ch * 4])), __float_as_uint(from_f32<float>(pv[ch * 4 + 1])),
-                              __float_as_uint(from_f32<float>(pv[ch * 4 + 2])), __float_as_uint(from_f32<float>(pv[ch * 4 + 3])));
-          }
+          v[i] = __float_as_uint(from_f32<float>(p0)); v[i + 1] = __float_as_uint(from_f32<float>(p1));
         }
       }
-      const float rs = rs0 + rs1;
-      tc_fence_before();
-      fence_proxy_async();
-      mbar_arrive(p_ready);
-      l_run = l_run * alpha + rs;
-      m_run = mx;
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kHeadDim; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_O + lane_off + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c + i] = o_acc[c + i] * alpha + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-      mbar_arrive(o_free);
-    }
-    if (q0 + r < p.n_tokens) {
-      const float inv = 1.f / l_run;
-      T* dst = p.out + ((size_t)b * p.n_tokens + q0 + r) * 512 + h * kHeadDim;
+      l_run += rs0 + rs1;
+      if (j > 0 && !o_waited) mbar_wait(o_full, (j - 1) & 1);   // P V(j-1) no longer reads the P tile
+      // write this row's probabilities into the swizzled K-major P tile (operand precision)
       if constexpr (sizeof(T) == 2) {
 #pragma unroll
-        for (int c = 0; c < kHeadDim; c += 8) {
-          uint32_t w[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(o_acc[c + 2 * t] * inv, o_acc[c + 2 * t + 1] * inv);
-            w[t] = *reinterpret_cast<uint32_t*>(&h2);
-          }
-          *reinterpret_cast<uint4*>(dst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int ch = 0; ch < BKV / 8; ++ch) {    // 16-byte chunks of 8 keys; 8 chunks per 128-byte atom row
+          const int atom = ch / 8, cc = ch % 8;
+          uint4* dst = reinterpret_cast<uint4*>(sP + atom * 128 * 128 + r * 128 + ((cc ^ (r & 7)) * 16));
+          *dst = make_uint4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < kHeadDim; c += 4)
-          *reinterpret_cast<float4*>(dst + c) =
-              make_float4(o_acc[c] * inv, o_acc[c + 1] * inv, o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+        for (int ch = 0; ch < BKV / 4; ++ch) {    // 16-byte chunks of 4 keys; 8 chunks per 128-byte atom row (32 keys)
+          const int atom = ch / 8, cc = ch % 8;
+          uint4* dst = reinterpret_cast<uint4*>(sP + atom * 128 * 128 + r * 128 + ((cc ^ (r & 7)) * 16));
+          *dst = make_uint4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(p_ready);
+    }
+    // O is complete in TMEM: normalise and store
+    mbar_wait(o_full, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const bool valid = q0 + r < p.n_tokens;
+    T* dst = p.out + ((size_t)b * p.n_tokens + q0 + r) * 512 + h * kHeadDim;
+#pragma unroll
+    for (int c = 0; c < kHeadDim; c += 32) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_off + c, o);
+      tmem_ld_wait();
+      if (valid) {
+        if constexpr (sizeof(T) == 2) {
+#pragma unroll
+          for (int c8 = 0; c8 < 32; c8 += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(o[c8 + 2 * t]) * inv, __uint_as_float(o[c8 + 2 * t + 1]) * inv);
+              w[t] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(dst + c + c8) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
+#pragma unroll
+          for (int c4 = 0; c4 < 32; c4 += 4)
+            *reinterpret_cast<float4*>(dst + c + c4) =
+                make_float4(__uint_as_float(o[c4]) * inv, __uint_as_float(o[c4 + 1]) * inv, __uint_as_float(o[c4 + 2]) * inv,
+                            __uint_as_float(o[c4 + 3]) * inv);
+        }
       }
     }
+    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
