@@ -174,4 +174,264 @@ __global__ void __launch_bounds__(256) d0_up_kernel(const T* __restrict__ c, con
   v[(size_t)b * L + l] = x[(size_t)(b % Bx) * L + l] + s * acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------- fused depth-0 item
+// The six reference ops of a depth-0 item (GN1+SiLU, conv1, GN2+SiLU, conv2 + x, Modulation, InjectChannels) in TWO
+// launches - the GroupNorm statistics of conv1's output are the only full-length dependency inside the item:
+//   d0_gn_conv1 : h = conv3(SiLU(GN1(x))) + b1                        x fp32 -> h operand dtype (+ GN2 sums)
+//   d0_tail     : y = Inject(Mod(LN(conv3(SiLU(GN2(h))) + b2 + x)))   h, x -> y fp32 in place (+ operand copy, GN sums)
+// Every tensor crosses HBM once per launch (700 -> ~400 MB per item at B = 16); activations between the fused steps
+// stay in fp32 registers / shared memory, so the result is at least as close to the fp32 reference as the unfused path.
+//
+// Tiling: a block of 256 threads covers kD0Rows = 768 consecutive positions base - 1 .. base + 766 (three per thread,
+// all loads issued up front), activates them into shared memory (row pitch 12 floats: conflict-free 128-bit
+// accesses) and produces the 766 outputs base .. base + 765 - the conv halo costs no separate loads.  The conv keeps
+// the three positions of a thread in registers so every weight vector read from shared memory feeds 24 FMAs (the
+// kernels are instruction-issue bound, not HBM bound: ncu 54 % issue slots busy at 1.4 TB/s before this layout).
+constexpr int kD0Per = 3;
+constexpr int kD0Rows = 256 * kD0Per;
+constexpr int kD0Pitch = 12;
+__host__ __device__ constexpr int d0_positions_per_block() { return kD0Rows - 2; }
+
+struct D0Smem {
+  float t[kD0Rows * kD0Pitch];
+  float w[24 * 8];
+  float ab[16];        // per-channel y = x * a + b of the GroupNorm in front of the conv
+  double red[16];
+};
+
+__device__ __forceinline__ float silu_fast(float y) { return __fdividef(y, 1.f + __expf(-y)); }
+
+// per-channel GroupNorm coefficients from the fp64 sums (depth 0: 8 groups over 8 channels = instance norm)
+__device__ __forceinline__ void d0_coef(D0Smem& sm, const double* stats_b, const float* gamma, const float* beta, int L, float eps) {
+  const int tid = threadIdx.x;
+  if (tid < 8) {
+    const double cnt = (double)L;
+    const double mean = stats_b[tid * 2] / cnt;
+    double var = stats_b[tid * 2 + 1] / cnt - mean * mean;
+    var = var > 0 ? var : 0;
+    const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[tid];
+    sm.ab[tid] = a;
+    sm.ab[8 + tid] = beta[tid] - (float)mean * a;
+  }
+  if (tid < 16) sm.red[tid] = 0.0;
+}
+__device__ __forceinline__ void d0_act_row(const D0Smem& sm, const float* x, float* row) {
+  float t[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = silu_fast(x[j] * sm.ab[j] + sm.ab[8 + j]);
+  *reinterpret_cast<float4*>(row) = make_float4(t[0], t[1], t[2], t[3]);
+  *reinterpret_cast<float4*>(row + 4) = make_float4(t[4], t[5], t[6], t[7]);
+}
+__device__ __forceinline__ void d0_zero_row(float* row) {
+  *reinterpret_cast<float4*>(row) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(row + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// acc[k][8] += conv3 over the activated rows around tile rows tid + 256 k (k < 3); tile row r is position base - 1 + r.
+// Rows are clamped into the tile: the two edge rows (0 and kD0Rows - 1) compute garbage that is never stored.
+__device__ __forceinline__ void d0_conv3x3(const D0Smem& sm, int tid, float (*acc)[8]) {
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    float xv[kD0Per][8];
+#pragma unroll
+    for (int k = 0; k < kD0Per; ++k) {
+      int r = tid + 256 * k + t - 1;
+      r = r < 0 ? 0 : (r > kD0Rows - 1 ? kD0Rows - 1 : r);
+      const float4 x0 = *reinterpret_cast<const float4*>(&sm.t[r * kD0Pitch]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&sm.t[r * kD0Pitch + 4]);
+      xv[k][0] = x0.x; xv[k][1] = x0.y; xv[k][2] = x0.z; xv[k][3] = x0.w; xv[k][4] = x1.x; xv[k][5] = x1.y; xv[k][6] = x1.z; xv[k][7] = x1.w;
+    }
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&sm.w[(t * 8 + ci) * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&sm.w[(t * 8 + ci) * 8 + 4]);
+#pragma unroll
+      for (int k = 0; k < kD0Per; ++k) {
+        acc[k][0] += xv[k][ci] * w0.x; acc[k][1] += xv[k][ci] * w0.y; acc[k][2] += xv[k][ci] * w0.z; acc[k][3] += xv[k][ci] * w0.w;
+        acc[k][4] += xv[k][ci] * w1.x; acc[k][5] += xv[k][ci] * w1.y; acc[k][6] += xv[k][ci] * w1.z; acc[k][7] += xv[k][ci] * w1.w;
+      }
+    }
+  }
+}
+// block-level flush of per-thread (sum, sum of squares) of 8 channels: fp32 over the thread's <= 3 positions, fp64 from
+// there on (GroupNorm at depth 0 is a per-channel instance norm; E[x^2] - mean^2 cancels catastrophically in fp32
+// whenever a channel is nearly constant, so every cross-position accumulation is done in double).
+__device__ __forceinline__ void d0_flush_stats(D0Smem& sm, const float* fa, const float* fq, double* stats_b) {
+  double sa[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sa[j] = (double)fa[j]; sq[j] = (double)fq[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], o); sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], o); }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&sm.red[j * 2], sa[j]); atomicAdd(&sm.red[j * 2 + 1], sq[j]); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) atomicAdd(&stats_b[threadIdx.x], sm.red[threadIdx.x]);
+}
+
+template <typename T> struct RawVec8;
+template <> struct RawVec8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void get(float* v) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+};
+template <> struct RawVec8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float* v) const {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+  }
+};
+
+// x [B, L, 8] f32 -> h [B, L, 8] (T) ; w [24][8] f32 (k = tap * 8 + ci, co fastest)
+template <typename T>
+__global__ void __launch_bounds__(256, 3) d0_gn_conv1_kernel(const float* __restrict__ x, const double* __restrict__ stats_in,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             T* __restrict__ out_t, double* __restrict__ stats_out, int L, float eps) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ D0Smem sm;
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const float* xb = x + (size_t)b * L * 8;
+  const int base = blockIdx.x * d0_positions_per_block();
+  RawVec8<float> raw[kD0Per];
+#pragma unroll
+  for (int k = 0; k < kD0Per; ++k) {
+    const int l = base - 1 + tid + 256 * k;
+    if (l >= 0 && l < L) raw[k].load(xb + (size_t)l * 8);
+  }
+  d0_coef(sm, stats_in + (size_t)b * 16, gamma, beta, L, eps);
+  if (tid < 192) sm.w[tid] = w[tid];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kD0Per; ++k) {
+    const int r = tid + 256 * k, l = base - 1 + r;
+    if (l >= 0 && l < L) { float xv[8]; raw[k].get(xv); d0_act_row(sm, xv, &sm.t[r * kD0Pitch]); }
+    else d0_zero_row(&sm.t[r * kD0Pitch]);
+  }
+  __syncthreads();
+  float acc[kD0Per][8];
+#pragma unroll
+  for (int k = 0; k < kD0Per; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = __ldg(&bias[j]);
+  d0_conv3x3(sm, tid, acc);
+  float fa[8], fq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { fa[j] = 0.f; fq[j] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < kD0Per; ++k) {
+    const int r = tid + 256 * k, l = base - 1 + r;
+    if (r >= 1 && r <= kD0Rows - 2 && l < L) {
+      store_operand8<T>(out_t + ((size_t)b * L + l) * 8, acc[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { fa[j] += acc[k][j]; fq[j] = fmaf(acc[k][j], acc[k][j], fq[j]); }
+    }
+  }
+  if (stats_out) d0_flush_stats(sm, fa, fq, stats_out + (size_t)b * 16);
+}
+
+// h [B, L, 8] (T), x / out_r [B, L, 8] f32 (in place), ctx [Bc, L, CTX] (T), mod = scale[8] | shift[8] of clip b % mod_bmod,
+// wi [8 + CTX][8] f32 (k, co), xbias [B, xb_stride] or null.
+template <typename T, int CTX>
+__global__ void __launch_bounds__(256, 3) d0_tail_kernel(const T* __restrict__ h, const double* __restrict__ stats_in,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         const float* x_r, const float* __restrict__ mod, int mod_bstride, int mod_bmod,
+                                                         const T* __restrict__ ctx, int Bc, const float* __restrict__ wi,
+                                                         const float* __restrict__ bi, const float* __restrict__ xbias, int xb_stride,
+                                                         float* out_r, T* __restrict__ out_t, double* __restrict__ stats_out, int L,
+                                                         float eps) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ D0Smem sm;
+  __shared__ float s_wi[(8 + CTX) * 8];
+  __shared__ float s_v[4 * 8];     // conv bias | 1 + mod scale | mod shift | inject bias + cross-attention bias
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const T* hb = h + (size_t)b * L * 8;
+  const float* xr = x_r + (size_t)b * L * 8;
+  const T* cb = ctx + (size_t)(b % Bc) * L * CTX;
+  const int base = blockIdx.x * d0_positions_per_block();
+  RawVec8<T> rh[kD0Per];
+  RawVec8<float> rr[kD0Per];
+  float rc[kD0Per][CTX];
+#pragma unroll
+  for (int k = 0; k < kD0Per; ++k) {
+    const int l = base - 1 + tid + 256 * k;
+    if (l >= 0 && l < L) {
+      rh[k].load(hb + (size_t)l * 8);
+      rr[k].load(xr + (size_t)l * 8);
+#pragma unroll
+      for (int ci = 0; ci < CTX; ++ci) rc[k][ci] = to_f32(cb[(size_t)l * CTX + ci]);
+    }
+  }
+  d0_coef(sm, stats_in + (size_t)b * 16, gamma, beta, L, eps);
+  if (tid < 192) sm.w[tid] = w[tid];
+  for (int i = tid; i < (8 + CTX) * 8; i += 256) s_wi[i] = wi[i];
+  if (tid < 8) {
+    const float* md = mod + (size_t)(b % mod_bmod) * mod_bstride;
+    s_v[tid] = bias[tid];
+    s_v[8 + tid] = 1.f + md[tid];
+    s_v[16 + tid] = md[8 + tid];
+    s_v[24 + tid] = bi[tid] + (xbias ? xbias[(size_t)b * xb_stride + tid] : 0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kD0Per; ++k) {
+    const int r = tid + 256 * k, l = base - 1 + r;
+    if (l >= 0 && l < L) { float xv[8]; rh[k].get(xv); d0_act_row(sm, xv, &sm.t[r * kD0Pitch]); }
+    else d0_zero_row(&sm.t[r * kD0Pitch]);
+  }
+  __syncthreads();
+  float acc[kD0Per][8];
+#pragma unroll
+  for (int k = 0; k < kD0Per; ++k) {
+    float r8[8];
+    rr[k].get(r8);                                     // residual x (garbage for out-of-range rows: never stored)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = r8[j] + s_v[j];
+  }
+  d0_conv3x3(sm, tid, acc);                            // r = conv2(SiLU(GN2(h))) + b2 + x
+  float fa[8], fq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { fa[j] = 0.f; fq[j] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < kD0Per; ++k) {
+    const int r = tid + 256 * k, l = base - 1 + r;
+    if (r >= 1 && r <= kD0Rows - 2 && l < L) {
+      const size_t g = ((size_t)b * L + l) * 8;
+      float mean = 0.f;                                // Modulation: LayerNorm over the 8 channels (two-pass), * (1 + s) + sh
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mean += acc[k][j];
+      mean *= 0.125f;
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = acc[k][j] - mean; var += d * d; }
+      const float rstd = rsqrtf(var * 0.125f + eps);
+      float m[8], y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { m[j] = (acc[k][j] - mean) * rstd * s_v[8 + j] + s_v[16 + j]; y[j] = m[j] + s_v[24 + j]; }
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] += m[ci] * s_wi[ci * 8 + j];
+#pragma unroll
+      for (int ci = 0; ci < CTX; ++ci)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] += rc[k][ci] * s_wi[(8 + ci) * 8 + j];
+      Vec8<float>::store(out_r + g, y);
+      if (out_t) store_operand8<T>(out_t + g, y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { fa[j] += y[j]; fq[j] = fmaf(y[j], y[j], fq[j]); }
+    }
+  }
+  if (stats_out) d0_flush_stats(sm, fa, fq, stats_out + (size_t)b * 16);
+}
+
 }  // namespace sfb

@@ -134,8 +134,8 @@ struct DepthW {
   int skip_off = 0;
 };
 
-enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN, OP_RK, OP_SK };
-const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn", "rk", "sk"};
+enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN, OP_RK, OP_SK, OP_D0_CONV1, OP_D0_TAIL };
+const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn", "rk", "sk", "d0_conv1", "d0_tail"};
 
 struct EngineBase {
   sfb_unet_config cfg;
@@ -257,6 +257,7 @@ struct Engine : EngineBase {
   int F_total = 0, XB_total = 0, n_gn = 0;
   bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aids: force the unfused generic path
   bool no_sk = getenv("SFB_NO_SK") != nullptr;
+  bool no_d0_fused = getenv("SFB_NO_D0_FUSED") != nullptr;
 #ifdef SFB_ENABLE_SK2
   bool no_sk2 = getenv("SFB_SK2") == nullptr;     // SFB_SK2=1: CTA-pair streaming-K kernel (sk2_tc.cuh) instead of the single-CTA one
 #else
@@ -273,6 +274,7 @@ struct Engine : EngineBase {
     double* stats_in = nullptr;
     double* stats_out = nullptr;
     const float *w0 = nullptr, *w1 = nullptr, *w2 = nullptr;
+    const float* wx[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // extra vectors of the fused depth-0 ops
     float fscalar = 0.f;
     int L = 0, C = 0, gs = 0, B = 0, taps = 1, in_is_f32 = 0, ctx = 0, k2 = 0;
     int ft_off = -1;      // feature-table column offset (Modulation scale | SkipModulate scale), -1: none
@@ -947,6 +949,20 @@ struct Engine : EngineBase {
           set_dbg(o, rows, C); plan.ops.push_back(o);
         }
       }
+    } else if (d == 0 && !no_d0_fused && ctx == 2) {
+      // ---- fused depth-0 item (d0.cuh): two launches, every tensor crosses HBM once per launch
+      {
+        Op o = base(OP_D0_CONV1, "conv1"); o.in = A; o.stats_in = cur; o.w0 = I.gn1_g; o.w1 = I.gn1_b; o.wx[0] = I.c8_w1; o.wx[1] = I.c8_b1;
+        o.out_t = T2; o.stats_out = sB;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
+      {
+        Op o = base(OP_D0_TAIL, "inject"); o.in = T2; o.stats_in = sB; o.w0 = I.gn2_g; o.w1 = I.gn2_b; o.wx[0] = I.c8_w2; o.wx[1] = I.c8_b2;
+        o.resid = A; o.out_r = A; o.ft_off = I.mod_off; o.in2 = at<T>(plan.lay.ctx[d]); o.ctx = ctx; o.wx[2] = I.c8_wi; o.wx[3] = I.c8_bi;
+        o.w2 = xb; o.out_t = want_t ? T1 : nullptr; o.stats_out = sOut;
+        if (want_t) item_t_out = T1;
+        set_dbg(o, rows, C); plan.ops.push_back(o);
+      }
     } else {
       {  // gn1 + SiLU
         Op o = base(OP_GN, "gn1"); o.in = A; o.in_is_f32 = 1; o.stats_in = cur; o.w0 = I.gn1_g; o.w1 = I.gn1_b; o.out_t = T1;
@@ -1170,6 +1186,12 @@ struct Engine : EngineBase {
       } else if (o.kind == OP_INJ_C8) {
         flops = 2.0 * rows * 8 * (8 + o.ctx);
         bytes = rows * (8 * (sizeof(T) + 4) + o.ctx * sizeof(T) + 8 * ((o.out_r ? 4 : 0) + (o.out_t ? sizeof(T) : 0)));
+      } else if (o.kind == OP_D0_CONV1) {
+        flops = 2.0 * rows * 8 * 24;
+        bytes = rows * 8 * (4 + sizeof(T));
+      } else if (o.kind == OP_D0_TAIL) {
+        flops = 2.0 * rows * 8 * (24 + 8 + o.ctx);
+        bytes = rows * (8 * (sizeof(T) + 4 + 4 + (o.out_t ? sizeof(T) : 0)) + o.ctx * sizeof(T));
       } else if (o.kind == OP_D0_DOWN) {
         flops = 2.0 * rows * 8;
         bytes = rows * (4 + 32);
@@ -1295,6 +1317,16 @@ struct Engine : EngineBase {
           launch_pdl(inject_c8_kernel<T, 2>, dim3(lb, o.B), 256, 0, st, reinterpret_cast<const T*>(o.in), o.resid,
                                                                reinterpret_cast<const T*>(o.in2), o.w0, o.w1, o.w2, o.out_r,
                                                                reinterpret_cast<T*>(o.out_t), o.stats_out, o.L, Bx, XB_total);
+          break;
+        case OP_D0_CONV1:
+          launch_pdl(d0_gn_conv1_kernel<T>, dim3((unsigned)((o.L + d0_positions_per_block() - 1) / d0_positions_per_block()), o.B), 256, 0, st, reinterpret_cast<const float*>(o.in),
+                     (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], reinterpret_cast<T*>(o.out_t), o.stats_out, o.L, 1e-5f);
+          break;
+        case OP_D0_TAIL:
+          launch_pdl(d0_tail_kernel<T, 2>, dim3((unsigned)((o.L + d0_positions_per_block() - 1) / d0_positions_per_block()), o.B), 256, 0, st, reinterpret_cast<const T*>(o.in),
+                     (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], o.resid, sc.frow + o.ft_off, sc.bstride, sc.bmod,
+                     reinterpret_cast<const T*>(o.in2), Bx, o.wx[2], o.wx[3], o.w2, XB_total, o.out_r, reinterpret_cast<T*>(o.out_t),
+                     o.stats_out, o.L, 1e-5f);
           break;
         case OP_D0_UP:
           launch_pdl(d0_up_kernel<T>, dim3(lb, o.B), 256, 0, st, reinterpret_cast<const T*>(o.in), o.w0, o.fscalar, sc.frow + o.ft_off,
