@@ -127,14 +127,12 @@ struct RkCfg {
   static constexpr int OP_BYTES = KA * ATOM_A;
   static constexpr int RAW_ATOMS = K1 / 32;
   static constexpr int RAW_BYTES = XF == 2 ? RAW_ATOMS * ATOM_A : 0;
-  static constexpr int NSA = 2;
   static constexpr int W1_TILES = TAPS * KA;
   static constexpr int KA2 = EPI == 2 ? (N + 64) / 64 : 0;   // chained K = [m (N) | ctx]: ctx <= 32 if N == 32, <= 64 if N == 64
   static constexpr int W_BYTES = (W1_TILES + KA2) * N * 128;
   static constexpr int RA = N / 32;
   static constexpr int R_BYTES = USE_R ? RA * 128 * 128 : 0;
-  static constexpr int CTX_BYTES = EPI == 2 ? (N == 64 ? 4096 : 8192) : 0;   // dense [128 rows][ctx * 2 B]: ctx <= 16 (N = 64) / 32 (N = 32)
-  static constexpr int NSR = 3;
+  static constexpr int CTX_BYTES = EPI == 2 ? 4096 : 0;   // dense [128 rows][ctx * 2 B]: ctx <= 16
   static constexpr int TA = (N + 63) / 64;
   static constexpr int T_BYTES = EPI == 2 ? 0 : TA * 128 * 128;   // chain: the bf16 output copy aliases the A2 buffer
   static constexpr int A2_BYTES = KA2 * 128 * 128;
@@ -144,6 +142,15 @@ struct RkCfg {
   static constexpr int EPI_WARP0 = XF ? 6 : 2;
   static constexpr int TMEM_NEED = EPI == 2 ? 3 * N : 2 * N;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  // ring depths from the shared-memory budget: these kernels are HBM-latency bound (ncu: every role waits on TMA data at
+  // 28 % DRAM utilisation with two A stages), so whatever the resident weights leave goes into bytes in flight.
+  static constexpr int kBudget = 232448 - (W_BYTES + 2 * T_BYTES + A2_BYTES + VEC_FLOATS * 4 + 256 + 1024);
+  static constexpr int PER_A = OP_BYTES + RAW_BYTES;
+  static constexpr int PER_R = R_BYTES + CTX_BYTES;
+  static constexpr int NSR_FIT = PER_R > 0 ? (kBudget - 2 * PER_A) / PER_R : 3;
+  static constexpr int NSR = NSR_FIT >= 5 ? 5 : (NSR_FIT >= 4 ? 4 : 3);
+  static constexpr int NSA_FIT = (kBudget - NSR * PER_R) / PER_A;
+  static constexpr int NSA = NSA_FIT >= 4 ? 4 : (NSA_FIT >= 3 ? 3 : 2);
   // smem carve-up (every tile region is a multiple of 1024 B)
   static constexpr int OFF_W = 0;
   static constexpr int OFF_OP = OFF_W + W_BYTES;
@@ -175,17 +182,18 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
   uint8_t* sA2 = smem + C::OFF_A2;
   float* sVEC = reinterpret_cast<float*>(smem + C::OFF_VEC);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  constexpr int NSA = C::NSA;
   uint64_t* w_full = bars + 0;
-  uint64_t* a_full = bars + 1;       // [2]   TMA -> transform (XF) / MMA
-  uint64_t* a_empty = bars + 3;      // [2]   MMA commit -> TMA
-  uint64_t* op_full = bars + 5;      // [2]   transform -> MMA
-  uint64_t* acc1_full = bars + 7;    // [2]   MMA commit -> epilogue
-  uint64_t* acc1_empty = bars + 9;   // [2]   epilogue -> MMA
-  uint64_t* a2_full = bars + 11;     //       epilogue -> MMA (chained operand written)
-  uint64_t* acc2_full = bars + 12;   //       MMA commit -> epilogue
-  uint64_t* r_full = bars + 13;      // [3]   TMA -> epilogue (residual + context tile)
-  uint64_t* r_empty = bars + 16;     // [3]   epilogue (store has read the tile) -> TMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* a_full = bars + 1;       // [NSA <= 4]   TMA -> transform (XF) / MMA
+  uint64_t* a_empty = bars + 5;      // [NSA]        MMA commit -> TMA
+  uint64_t* op_full = bars + 9;      // [NSA]        transform -> MMA
+  uint64_t* acc1_full = bars + 13;   // [2]   MMA commit -> epilogue
+  uint64_t* acc1_empty = bars + 15;  // [2]   epilogue -> MMA
+  uint64_t* a2_full = bars + 17;     //       epilogue -> MMA (chained operand written)
+  uint64_t* acc2_full = bars + 18;   //       MMA commit -> epilogue
+  uint64_t* r_full = bars + 19;      // [NSR <= 5]   TMA -> epilogue (residual + context tile)
+  uint64_t* r_empty = bars + 24;     // [NSR]        epilogue (store has read the tile) -> TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous tile range per CTA: a CTA stays inside one clip as long as possible (few statistic flushes)
@@ -197,10 +205,8 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmW);
     mbar_init(w_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&op_full[s], 128);
-      mbar_init(&acc1_full[s], 1); mbar_init(&acc1_empty[s], 128);
-    }
+    for (int s = 0; s < NSA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&op_full[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&acc1_empty[s], 128); }
     for (int s = 0; s < NSR; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
     mbar_init(a2_full, 128);
     mbar_init(acc2_full, 1);
@@ -228,8 +234,8 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
       for (int t = t_begin; t < t_end; ++t, ++i) {
         const int b = t / p.tiles_per_clip;
         const int l0 = (t % p.tiles_per_clip) * 128;
-        const int s = i & 1;
-        mbar_wait(&a_empty[s], ((i >> 1) & 1) ^ 1);
+        const int s = i % NSA;
+        mbar_wait(&a_empty[s], ((i / NSA) & 1) ^ 1);
         if (XF == 2) {
           mbar_expect_tx(&a_full[s], C::RAW_BYTES);
           for (int a = 0; a < C::RAW_ATOMS; ++a)
@@ -267,12 +273,12 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
       };
       uint32_t i = 0;
       for (int t = t_begin; t < t_end; ++t, ++i) {
-        const int s = i & 1;
-        mbar_wait(XF ? &op_full[s] : &a_full[s], (i >> 1) & 1);
+        const int s = i & 1, sa = i % NSA;
+        mbar_wait(XF ? &op_full[sa] : &a_full[sa], (i / NSA) & 1);
         mbar_wait(&acc1_empty[s], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + s * N;
-        const uint32_t opb = smem_u32(sOP + s * C::OP_BYTES), wb = smem_u32(sW);
+        const uint32_t opb = smem_u32(sOP + sa * C::OP_BYTES), wb = smem_u32(sW);
         bool first = true;
 #pragma unroll
         for (int tap = 0; tap < TAPS; ++tap) {
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
             }
           }
         }
-        umma_commit(&a_empty[s]);
+        umma_commit(&a_empty[sa]);
         umma_commit(&acc1_full[s]);
         if (EPI == 2 && i > 0) issue_mma2(i - 1);
       }
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
     for (int t = t_begin; t < t_end; ++t, ++i) {
       const int b = t / p.tiles_per_clip;
       const int l0 = (t % p.tiles_per_clip) * 128;
-      const int s = i & 1;
+      const int s = i % NSA;
       if (b != cur_b) {
         cur_b = b;
         const double inv_cnt = 1.0 / ((double)p.L * GSA);   // fp64 only where E[x^2] - mean^2 cancels; no fp64 div / sqrt per channel
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
 #pragma unroll
         for (int j = 0; j < 4; ++j) gn_pack_coef(ca[2 * j], cb[2 * j], ca[2 * j + 1], cb[2 * j + 1], pa[j], pbh[j], pbl[j]);
       }
-      mbar_wait(&a_full[s], (i >> 1) & 1);
+      mbar_wait(&a_full[s], (i / NSA) & 1);
       uint8_t* op = sOP + s * C::OP_BYTES + (g / 8) * C::ATOM_A;
       const int co = g % 8;
       constexpr int NIT = (C::ROWS_A + RPI - 1) / RPI;
@@ -637,7 +643,7 @@ inline RkKey rk_key(int id) {
   };
   return keys[id];
 }
-inline int rk_ctx_capacity(int N) { return N == 64 ? 16 : 32; }   // context channels the chained operand / staging tile can take
+inline int rk_ctx_capacity(int N) { (void)N; return 16; }   // context channels the chained operand / staging tile can take
 
 inline cudaError_t rk_set_attrs() {
   cudaError_t e = cudaSuccess;
