@@ -1226,6 +1226,17 @@ struct Engine : EngineBase {
     fold_items.clear(); fold_next = 0; fold_rows = 0;
     rc = build_block(0);
     if (rc) { plan.ops.clear(); return rc; }
+    if constexpr (kBF16) {      // shared-memory ring depths / epilogue width of every streaming-K op (sk_tc.cuh)
+      const bool no_epi12 = getenv("SFB_NO_EPI12") != nullptr;
+      for (Op& o : plan.ops) {
+        if (o.kind != OP_SK) continue;
+        SkParams& q = o.sp;
+        q.epi12 = (!no_epi12 && q.xf == 0 && q.taps == 1 && q.rowstats_out == nullptr) ? 1 : 0;   // the small-K, epilogue-bound ops
+        const bool uses_r = q.resid_mode != 0 || q.has_out_r != 0;
+        if (o.BN == 256) sk_pick_rings<256>(q.taps, q.xf, uses_r, q.epi12, q.na, q.nb, q.nr);
+        else sk_pick_rings<128>(q.taps, q.xf, uses_r, q.epi12, q.na, q.nb, q.nr);
+      }
+    }
     if (!fold_items.empty()) {
       if (fold_items.size() > fold_items_cap) {
         void* d = nullptr;

@@ -55,33 +55,44 @@ struct SkParams {
   float* rowstats_out;          // [B * L, n_tiles, 2] or null
   int L, tiles_per_clip, N, n_tiles, total_tiles, taps, k1_chunks, k2_chunks, K1, a2_bmod;
   float eps;
+  // shared-memory ring depths of this op (host: sk_pick_rings) and the epilogue width
+  int na, nb, nr;               // A / weight / residual stages
+  int epi12;                    // xf == 0 ops: the four idle A-transform warps join the epilogue (12 warps, three chunk groups)
   long long* dbg;               // optional timeline buffer (CTA 0 only): [role][256] clock64 stamps (tools/sk_timeline.py)
 };
 
 #define SK_STAMP(role, idx) do { if (p.dbg != nullptr && blockIdx.x == 0 && (idx) < 256) p.dbg[(role) * 256 + (idx)] = clock64(); } while (0)
 
 template <int BN> struct SkCfg {
-  static constexpr int NA = BN == 256 ? 2 : 3;
-  static constexpr int NB = BN == 256 ? 3 : 5;
-  static constexpr int NR = 4;                 // residual / fp32-out chunk ring (in place)
-  static constexpr int NT = 2;                 // bf16-out chunk ring
   static constexpr int A_BYTES = 136 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int R_BYTES = 128 * 128;    // [128 rows][32 fp32], 128B swizzle
-  static constexpr int T_BYTES = 128 * 64;     // [4 lane quarters][32 rows][32 bf16], 64B swizzle, one per chunk parity
+  static constexpr int T_WARP = 2048;          // per epilogue warp: [32 rows][32 bf16], 64B swizzle
   static constexpr int KMAX = 1024;            // largest transformed K1
-  static constexpr int OFF_A = 0;
-  static constexpr int OFF_B = OFF_A + NA * A_BYTES;
-  static constexpr int OFF_R = OFF_B + NB * B_BYTES;
-  static constexpr int OFF_T = OFF_R + NR * R_BYTES;
-  static constexpr int OFF_TAB = OFF_T + NT * T_BYTES;         // [2][KMAX] per-channel transform coefficients
-  static constexpr int OFF_ROWTAB = OFF_TAB + 2 * KMAX * 4;    // [136][2] per-row mean, rstd
-  static constexpr int OFF_VEC = OFF_ROWTAB + 2 * 136 * 4 + 64;
-  static constexpr int OFF_BAR = OFF_VEC + 5 * BN * 4;
-  static constexpr int SMEM = OFF_BAR + 512;
+  static constexpr int MAX_NA = 4, MAX_NB = 6, MAX_NR = 6;
+  // fixed part behind the rings: bf16 staging (8 or 12 warps) | coefficient tables | row table | epilogue vectors | barriers
+  static constexpr int TAB_BYTES = 2 * KMAX * 4, ROWTAB_BYTES = 2 * 136 * 4 + 64, VEC_BYTES = 5 * BN * 4, BAR_BYTES = 512;
+  __host__ __device__ static constexpr int fixed_bytes(int epi12) { return (epi12 ? 12 : 8) * T_WARP + TAB_BYTES + ROWTAB_BYTES + VEC_BYTES + BAR_BYTES; }
+  __host__ __device__ static constexpr int smem_bytes(int na, int nb, int nr, int epi12) {
+    return na * A_BYTES + nb * B_BYTES + nr * R_BYTES + fixed_bytes(epi12);
+  }
   static constexpr int kThreads = 512;
-  static_assert(SMEM <= 232448, "shared memory budget");
+  static constexpr int kMaxSmem = 232448;
 };
+// Ring depths per op class under the 227 KB budget (host side).  The mainloop of the k = 3 convs wants A stages (load ->
+// in-place transform -> MMA each hold one), the HBM-bound 1 x 1 ops want residual chunks in flight.
+template <int BN>
+inline void sk_pick_rings(int taps, int xf, bool uses_r, int epi12, int& na, int& nb, int& nr) {
+  using C = SkCfg<BN>;
+  if (taps == 3) { na = uses_r ? 3 : 4; nr = uses_r ? 3 : 0; }
+  else if (epi12) { na = uses_r ? 2 : 3; nr = uses_r ? 5 : 0; }
+  else { na = 2; nr = uses_r ? 4 : 0; }
+  auto fits = [&](int a, int b2, int r) { return C::smem_bytes(a, b2, r, epi12) <= C::kMaxSmem; };
+  nb = taps == 3 ? C::MAX_NB : na + 1;      // one weight tile per tap: a 1 x 1 op never runs further ahead on B than on A
+  while (nb > 2 && !fits(na, nb, nr)) --nb;
+  while (!fits(na, nb, nr) && nr > 2) --nr;
+  while (!fits(na, nb, nr) && na > 2) --na;
+}
 
 // EPI: compile-time epilogue shape (the per-column math sits in the hottest loop of the small-K ops, where uniform
 // run-time branches cost a third of the issue slots and pin every shared-memory load behind a branch):
@@ -95,27 +106,28 @@ template <int BN, int GS, int EPI>
 __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkParams p) {
   pdl_trigger();
   using C = SkCfg<BN>;
-  constexpr int NA = C::NA, NB = C::NB, NR = C::NR, NT = C::NT;
+  const int NA = p.na, NB = p.nb, NR = p.nr;          // ring depths of this op (uniform)
+  const bool epi12 = p.epi12 != 0;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem + C::OFF_A;
-  uint8_t* sB = smem + C::OFF_B;
-  uint8_t* sR = smem + C::OFF_R;
-  uint8_t* sT = smem + C::OFF_T;
-  float* tab_a = reinterpret_cast<float*>(smem + C::OFF_TAB);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + NA * C::A_BYTES;
+  uint8_t* sR = sB + NB * C::B_BYTES;
+  uint8_t* sT = sR + NR * C::R_BYTES;
+  float* tab_a = reinterpret_cast<float*>(sT + (epi12 ? 12 : 8) * C::T_WARP);
   float* tab_b = tab_a + C::KMAX;
-  float* rowtab = reinterpret_cast<float*>(smem + C::OFF_ROWTAB);
-  float* sVEC = reinterpret_cast<float*>(smem + C::OFF_VEC);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* a_full = bars;                 // [NA]
-  uint64_t* a_empty = a_full + NA;         // [NA]
-  uint64_t* op_full = a_empty + NA;        // [NA]
-  uint64_t* b_full = op_full + NA;         // [NB]
-  uint64_t* b_empty = b_full + NB;         // [NB]
-  uint64_t* acc_full = b_empty + NB;       // [2]
-  uint64_t* acc_empty = acc_full + 2;      // [2]
-  uint64_t* rc_full = acc_empty + 2;       // [NR]
-  uint64_t* rc_empty = rc_full + NR;       // [NR]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rc_empty + NR);
+  float* rowtab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tab_a) + C::TAB_BYTES);
+  float* sVEC = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(rowtab) + C::ROWTAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sVEC) + C::VEC_BYTES);
+  uint64_t* a_full = bars;                       // [NA]
+  uint64_t* a_empty = a_full + C::MAX_NA;        // [NA]
+  uint64_t* op_full = a_empty + C::MAX_NA;       // [NA]
+  uint64_t* b_full = op_full + C::MAX_NA;        // [NB]
+  uint64_t* b_empty = b_full + C::MAX_NB;        // [NB]
+  uint64_t* acc_full = b_empty + C::MAX_NB;      // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint64_t* rc_full = acc_empty + 2;             // [NR]
+  uint64_t* rc_empty = rc_full + C::MAX_NR;      // [NR]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rc_empty + C::MAX_NR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_begin = (int)(((long long)p.total_tiles * blockIdx.x) / gridDim.x);
@@ -129,7 +141,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
     tma_prefetch_desc(&p.tmW);
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&op_full[s], 128); }
     for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 256); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], epi12 ? 384 : 256); }
     for (int s = 0; s < NR; ++s) { mbar_init(&rc_full[s], 1); mbar_init(&rc_empty[s], 4); }
     fence_barrier_init();
   }
@@ -145,6 +157,8 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
     if (lane == 0) {
       // ------------------------------------------------------------- mainloop TMA producer
       uint32_t ia = 0, ib = 0;
+      int sa = 0, sb = 0;                 // ring slots and phases advance incrementally (the depths are run-time values:
+      uint32_t pha = 0, phb = 0;          // a division per k chunk on this single thread would cost more than the TMA issue)
       for (int t = t_begin; t < t_end; ++t) {
         const int n0 = (t % p.n_tiles) * BN;
         const int mi = t / p.n_tiles;
@@ -153,8 +167,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         const int wcopy = b % p.w_bmod;
         for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
           const bool second = kc >= p.k1_chunks;
-          const int sa = ia % NA;
-          mbar_wait(&a_empty[sa], ((ia / NA) & 1) ^ 1);
+          mbar_wait(&a_empty[sa], pha ^ 1);
           if (!second) {
             mbar_expect_tx(&a_full[sa], rows_a * 128);
             tma_load_3d(sA + sa * C::A_BYTES, &p.tmA1, &a_full[sa], kc * 64, l0 - pad, b);
@@ -165,12 +178,13 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           SK_STAMP(0, ia);
           const int ntap = second ? 1 : p.taps;
           for (int tap = 0; tap < ntap; ++tap, ++ib) {
-            const int sb = ib % NB;
-            mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
+            mbar_wait(&b_empty[sb], phb ^ 1);
             mbar_expect_tx(&b_full[sb], C::B_BYTES);
             tma_load_3d(sB + sb * C::B_BYTES, &p.tmW, &b_full[sb], second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64, tap * p.N + n0, wcopy);
             SK_STAMP(1, ib);
+            if (++sb == NB) { sb = 0; phb ^= 1; }
           }
+          if (++sa == NA) { sa = 0; pha ^= 1; }
         }
       }
     }
@@ -179,6 +193,8 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       // ------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, BN, 0, 0);
       uint32_t ia = 0, ib = 0, i = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       for (int t = t_begin; t < t_end; ++t, ++i) {
         const uint32_t acc = i & 1;
         mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
@@ -187,16 +203,14 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         bool first = true;
         for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
           const bool second = kc >= p.k1_chunks;
-          const int sa = ia % NA;
-          mbar_wait(&a_full[sa], (ia / NA) & 1);
-          if (p.xf) mbar_wait(&op_full[sa], (ia / NA) & 1);
+          mbar_wait(&a_full[sa], pha);
+          if (p.xf) mbar_wait(&op_full[sa], pha);
           tc_fence_after();
           const uint32_t abase = smem_u32(sA + sa * C::A_BYTES);
           SK_STAMP(3, ia);
           const int ntap = second ? 1 : p.taps;
           for (int tap = 0; tap < ntap; ++tap, ++ib) {
-            const int sb = ib % NB;
-            mbar_wait(&b_full[sb], (ib / NB) & 1);
+            mbar_wait(&b_full[sb], phb);
             tc_fence_after();
             const uint32_t bbase = smem_u32(sB + sb * C::B_BYTES);
 #pragma unroll
@@ -206,8 +220,10 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
               first = false;
             }
             umma_commit(&b_empty[sb]);
+            if (++sb == NB) { sb = 0; phb ^= 1; }
           }
           umma_commit(&a_empty[sa]);
+          if (++sa == NA) { sa = 0; pha ^= 1; }
         }
         umma_commit(&acc_full[acc]);
       }
@@ -215,21 +231,22 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
   } else if (warp == 2) {
     if (lane == 0 && p.resid_mode != 0) {
       // ------------------------------------------------------------- epilogue TMA producer: residual chunks
-      uint32_t q = 0;
+      int rs = 0;
+      uint32_t phr = 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int n0 = (t % p.n_tiles) * BN;
         const int mi = t / p.n_tiles;
         const int b = mi / p.tiles_per_clip;
         const int l0 = (mi % p.tiles_per_clip) * 128;
-        for (int c = 0; c < NCH; ++c, ++q) {
-          const int rs = q % NR;
-          mbar_wait(&rc_empty[rs], ((q / NR) & 1) ^ 1);
+        for (int c = 0; c < NCH; ++c) {
+          mbar_wait(&rc_empty[rs], phr ^ 1);
           mbar_expect_tx(&rc_full[rs], C::R_BYTES);
           tma_load_3d(sR + rs * C::R_BYTES, &p.tmR, &rc_full[rs], n0 + c * 32, l0, b);
+          if (++rs == NR) { rs = 0; phr ^= 1; }
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 8 && !epi12) {
     if (p.xf) {
       // ------------------------------------------------------------- A transform (in place on the landed bf16 tile)
       const int tid = threadIdx.x - 128;        // 0..127
@@ -237,6 +254,8 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       const int rsub = tid >> 3;                 // 0..15
       int cur_b = -1, cur_mi = -1;
       uint32_t ia = 0;
+      int sa = 0;
+      uint32_t pha = 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int mi = t / p.n_tiles;
         const int b = mi / p.tiles_per_clip;
@@ -298,8 +317,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           named_bar(3, 128);
         }
         for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
-          const int sa = ia % NA;
-          mbar_wait(&a_full[sa], (ia / NA) & 1);
+          mbar_wait(&a_full[sa], pha);
           if (tid == 0) SK_STAMP(2, 2 * ia);
           if (p.xf == 3 ? kc >= p.k1_chunks : kc < p.k1_chunks) {
             uint8_t* tile = sA + sa * C::A_BYTES;
@@ -392,20 +410,24 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           }
           mbar_arrive(&op_full[sa]);
           if (tid == 0) SK_STAMP(2, 2 * ia + 1);
+          if (++sa == NA) { sa = 0; pha ^= 1; }
         }
       }
     }
-  } else if (warp >= 8) {
-    // ------------------------------------------------------------- epilogue: 8 warps, one accumulator row per thread.
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------- epilogue: 8 warps (12 with the idle transform warps of
+    // an xf == 0 op), one accumulator row per thread.
     // The two warps of a TMEM lane quarter (same SM sub-partition) take ALTERNATE 32-column chunks and own them end to
     // end: TMEM -> registers -> math -> private slice of the staging buffers -> own TMA stores (4 KB fp32 + 2 KB bf16
     // per store).  No CTA-level barrier in the chunk loop; the sibling warp hides TMEM / shared-memory / bulk-wait
     // latencies.  32-column chunks halve the per-column cost of the fixed per-chunk work (bulk wait, proxy fence,
     // store issue, barrier traffic) against 16-column ones and give every thread 32 independent values to work on.
     const int q4 = warp & 3;
-    const int par = (warp - 8) >> 2;
+    const int par = warp >= 8 ? (warp - 8) >> 2 : 2;        // chunk group: warps 8-11, 12-15, (4-7)
+    const int npar = epi12 ? 3 : 2;
+    const int nthr_epi = epi12 ? 384 : 256;
     const int row = q4 * 32 + lane;
-    const int et = threadIdx.x - 256;          // 0..255
+    const int et = warp >= 8 ? threadIdx.x - 256 : threadIdx.x + 128;     // 0..255, helpers 256..383
     const uint32_t lane_off = uint32_t(q4 * 32) << 16;
     const int resid_mode = EPI == 5 ? p.resid_mode : (EPI == 1 || EPI == 4) ? 1 : EPI == 3 ? 2 : 0;
     const bool ln_fold = EPI == 5 ? p.ln_fold != 0 : (EPI == 2 || EPI == 3);
@@ -416,7 +438,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
     float* ep_g = sVEC + 2 * BN;      // [BN] 1 + modulation scale   (resid_mode 2)
     float* ep_sh = sVEC + 3 * BN;     // [BN] modulation shift
     float* ep_ws = sVEC + 4 * BN;     // [BN] weight column sums (ln_fold)
-    uint8_t* tt = sT + (par * 4 + q4) * 2048;      // this warp's bf16 staging: [32 rows][64 B], 64B swizzle
+    uint8_t* tt = sT + (par * 4 + q4) * C::T_WARP; // this warp's bf16 staging: [32 rows][64 B], 64B swizzle
     float s1[8], s2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
@@ -439,6 +461,9 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
     };
     uint32_t i = 0;
     int prev_slot = -1;                 // R slot of this warp's previous chunk (handed back once its store was read)
+    int rs = 0;                         // R slot / phase of the chunk this warp works on (advanced by the chunk stride)
+    uint32_t phr = 0;
+    uint32_t q_cur = 0;                 // global chunk index rs / phr correspond to
     for (int t = t_begin; t < t_end; ++t, ++i) {
       const int n_idx = t % p.n_tiles;
       const int n0 = n_idx * BN;
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         const int goff = (n0 / GS) & 7;
         if (b != cur_b || goff != cur_goff) flush_stats(cur_b, cur_goff);
         cur_goff = goff;
-        named_bar(2, 256);
+        named_bar(2, nthr_epi);
         cur_b = b; cur_n = n_idx;
         for (int n = et; n < BN; n += 256) {
           const int nm = (n0 + n) % p.bias_mod;
@@ -486,7 +511,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
             ep_sh[n] = md[p.N + n0 + n];
           }
         }
-        named_bar(2, 256);
+        named_bar(2, nthr_epi);
       }
       float r_mean = 0.f, r_rstd = 0.f;
       if ((resid_mode == 2 || ln_fold) && row_valid) {     // LayerNorm statistics of this thread's A1 / residual row
@@ -506,9 +531,9 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
       const int sw7 = row & 7, sw3 = (lane >> 1) & 3;
       // The chunk loop is NOT unrolled: a fully unrolled epilogue is ~64 KB of SASS and misses the instruction cache.
 #pragma unroll 1
-      for (int c = par; c < NCH; c += 2) {
+      for (int c = par; c < NCH; c += npar) {
         const uint32_t qg = i * NCH + c;           // chunk counter shared with the residual producer
-        const int rs = qg % NR;
+        for (; q_cur < qg; ++q_cur) if (++rs == NR) { rs = 0; phr ^= 1; }
         uint8_t* rt = sR + rs * C::R_BYTES;         // [128 rows][128 B], 128B swizzle
         uint32_t v[32];
         tmem_ld32(tacc + c * 32, v);
@@ -518,11 +543,12 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         if (lane == 0) {
           bulk_wait_read<0>();
           if (resid_mode != 0 && prev_slot >= 0) mbar_arrive(&rc_empty[prev_slot]);
+          prev_slot = -1;
         }
         __syncwarp();
-        if (resid_mode != 0) mbar_wait(&rc_full[rs], (qg / NR) & 1);
+        if (resid_mode != 0) mbar_wait(&rc_full[rs], phr);
         tmem_ld_wait();
-        if (c + 2 >= NCH) {           // this thread's last TMEM read of the tile: hand the accumulator back
+        if (c + npar >= NCH) {        // this thread's last TMEM read of the tile: hand the accumulator back
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
         }
@@ -606,8 +632,12 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           if (has_out_t) tma_store_3d(&p.tmT, tt, n0 + c0, l0 + q4 * 32, b);
           bulk_commit();
           if (et == 0) SK_STAMP(4, 4 * (qg >> 1) + 3);
+          if (epi12 && resid_mode != 0) {      // three warps per sub-partition hide this wait; the slot returns a chunk earlier
+            bulk_wait_read<0>();
+            mbar_arrive(&rc_empty[rs]);
+          }
         }
-        prev_slot = rs;
+        prev_slot = epi12 ? -1 : rs;
       }
       if (p.rowstats_out != nullptr && row_valid) {      // two partial sums per (row, n tile): one per chunk parity
         float* dst = p.rowstats_out + (((size_t)b * p.L + l0 + row) * (2 * p.n_tiles) + 2 * n_idx + par) * 2;
@@ -639,7 +669,7 @@ inline int sk_find(int BN, int GS) {
 }
 inline cudaError_t sk_set_attrs() {
   cudaError_t e = cudaSuccess;
-#define Y(a, b, c) if (e == cudaSuccess) e = cudaFuncSetAttribute(sk_kernel<a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<a>::SMEM);
+#define Y(a, b, c) if (e == cudaSuccess) e = cudaFuncSetAttribute(sk_kernel<a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<a>::kMaxSmem);
 #define X(a, b) Y(a, b, 0) Y(a, b, 1) Y(a, b, 2) Y(a, b, 3) Y(a, b, 4) Y(a, b, 5)
   SFB_SK_LIST(X)
 #undef X
@@ -649,7 +679,7 @@ inline cudaError_t sk_set_attrs() {
 inline void sk_launch(int id, int epi, const SkParams& p, int num_sms, cudaStream_t st) {
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   int i = 0;
-#define Y(a, b, c) if (epi == c) { launch_pdl(sk_kernel<a, b, c>, grid, 512, SkCfg<a>::SMEM, st, p); return; }
+#define Y(a, b, c) if (epi == c) { launch_pdl(sk_kernel<a, b, c>, grid, 512, SkCfg<a>::smem_bytes(p.na, p.nb, p.nr, p.epi12), st, p); return; }
 #define X(a, b) if (id == i++) { Y(a, b, 0) Y(a, b, 1) Y(a, b, 2) Y(a, b, 3) Y(a, b, 4) Y(a, b, 5) }
   SFB_SK_LIST(X)
 #undef X
