@@ -5,7 +5,9 @@ import ctypes as C
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libsyncfusion_b200.so"
+import os
+
+LIB_PATH = Path(os.environ["SFB_LIB"]) if os.environ.get("SFB_LIB") else HERE / "libsyncfusion_b200.so"   # SFB_LIB: A/B a build
 SFB_MAX_DEPTH = 16
 
 EXPORTS = [

@@ -159,7 +159,6 @@ struct EngineBase {
   virtual int profile_report(char* buf, int len) = 0;
   virtual int sk_timeline(int op_index, long long* host_buf, int n) { (void)op_index; (void)host_buf; (void)n; return SFB_ERR_UNSUPPORTED; }
   bool profiling = false;
-  volatile unsigned long long* trap_record = nullptr;   // host side of g_sfb_trap_record
   int fail(int code, const char* fmt, ...) {
     char b[512];
     va_list ap;
@@ -167,13 +166,6 @@ struct EngineBase {
     vsnprintf(b, sizeof b, fmt, ap);
     va_end(ap);
     err = b;
-    if (code == SFB_ERR_CUDA && trap_record && trap_record[0] == 0x5346425f54524150ull) {
-      char t[256];
-      snprintf(t, sizeof t, " [barrier wait timed out: block (%llu,%llu,%llu) thread %llu of grid %llu x block %llu, mbarrier smem 0x%llx parity %llu]",
-               trap_record[1] >> 32, trap_record[4] >> 32, trap_record[4] & 0xffffffffull, trap_record[1] & 0xffffffffull,
-               trap_record[2] >> 32, trap_record[2] & 0xffffffffull, trap_record[3] >> 32, trap_record[3] & 0xffffffffull);
-      err += t;
-    }
     return code;
   }
 };
@@ -1243,6 +1235,10 @@ struct Engine : EngineBase {
         const bool uses_r = q.resid_mode != 0 || q.has_out_r != 0;
         if (o.BN == 256) sk_pick_rings<256>(q.taps, q.xf, uses_r, q.epi12, q.na, q.nb, q.nr);
         else sk_pick_rings<128>(q.taps, q.xf, uses_r, q.epi12, q.na, q.nb, q.nr);
+        if (getenv("SFB_RINGS_STATIC")) {      // A/B aid: the fixed depths of the first sk kernel
+          q.na = o.BN == 256 ? 2 : 3; q.nb = o.BN == 256 ? 3 : 5; q.nr = 4;
+          if (q.epi12 && SkCfg<256>::smem_bytes(q.na, q.nb, q.nr, 1) > SkCfg<256>::kMaxSmem && o.BN == 256) q.nr = 3;
+        }
       }
     }
     if (!fold_items.empty()) {
@@ -1570,16 +1566,6 @@ int sfb_create(const sfb_unet_config* cfg, int device, sfb_handle** out) {
   else h->e.reset(new Engine<float>());
   h->e->cfg = *cfg;
   h->e->device = device;
-  {   // host-mapped record the bounded barrier waits fill in before they trap (ptx.cuh: mbar_timeout)
-    unsigned long long* host = nullptr;
-    if (cudaHostAlloc(&host, 64, cudaHostAllocMapped) == cudaSuccess) {
-      memset(host, 0, 64);
-      unsigned long long* dptr = nullptr;
-      if (cudaHostGetDevicePointer(&dptr, host, 0) == cudaSuccess &&
-          cudaMemcpyToSymbol(g_sfb_trap_record, &dptr, sizeof dptr) == cudaSuccess)
-        h->e->trap_record = host;
-    }
-  }
   *out = h;
   return SFB_OK;
 }
