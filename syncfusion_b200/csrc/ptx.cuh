@@ -3,6 +3,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -60,11 +61,41 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // the NCCL all-gather, 50 steps).  The loop body must stay exactly this small: timer reads, a diagnostic record or an
 // out-of-line slow path at the ~25 wait sites of the 128-register kernels each made the whole sampling step 2-5 %
 // slower (A/B measured on the same box: 385 ms vs 394-406 ms per 16-clip step).
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes or ~1 ms
+// passed, so a waiting warp issues almost nothing (it does not compete with the working warps of its sub-partition) and
+// a poll parks for ~4 us on B200 whatever the hint says (tools/trywait_bench.cu), less when arrivals / TMA byte counts
+// keep waking the waiter.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
+      "selp.b32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+#ifdef SFB_WAIT_DEBUG      // diagnostic build: report waits that outlast 2^26 polls instead of trapping
+  unsigned long long t0 = 0;
+  while (!mbar_try_wait_hint(bar, parity)) {
+    if (spins == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    if (++spins == (1u << 26)) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      printf("[sfb long wait] 2^26 polls in %.3f s: block (%d,%d,%d)/%d thread %d/%d bar 0x%x parity %u\n", (t1 - t0) * 1e-9, blockIdx.x,
+             blockIdx.y, blockIdx.z, gridDim.x, threadIdx.x, blockDim.x, smem_u32(bar), parity);
+    }
+  }
+#else
+  while (!mbar_try_wait_hint(bar, parity)) {
     if (++spins > (1u << 31)) { __trap(); }
   }
+#endif
 }
 
 // ------------------------------------------------------------------ programmatic dependent launch (PDL)
