@@ -436,6 +436,59 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
                        pack_bf16(y[j8 * 8 + 4], y[j8 * 8 + 5]), pack_bf16(y[j8 * 8 + 6], y[j8 * 8 + 7]));
       }
     };
+    // Software-pipelined chain (EPI == 2 with >= 4 residual stages): the second epilogue of tile i-1 (acc2 of the chained
+    // inject MMA) runs AFTER the first epilogue of tile i, so the MMA round trip (a2_full -> issue -> commit -> acc2_full)
+    // is covered by LayerNorm work instead of idling the only epilogue warpgroup (ncu: 72 % no-eligible cycles).
+#ifdef SFB_RK_PIPE
+    constexpr bool PIPE = EPI == 2 && C::NSR >= 4;
+#else
+    constexpr bool PIPE = false;      // not yet verified on hardware: opt in with -DSFB_RK_PIPE
+#endif
+    bool pend = false;
+    int p_b = 0, p_l0 = 0, p_rs = 0;
+    bool p_valid = false;
+    uint32_t p_i = 0;
+    auto finish_tile = [&](int fb, int fl0, int frs, bool fvalid, uint32_t fi) {
+      uint8_t* rt = sR + frs * C::R_BYTES;
+      uint8_t* tt = sA2;
+      mbar_wait(acc2_full, fi & 1);
+      tc_fence_after();
+      const uint32_t tacc2 = tmem_base + 2 * N + lane_off;
+#pragma unroll
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tacc2 + c0, v);
+        tmem_ld_wait();
+        float y[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 ad = *reinterpret_cast<const float4*>(&ep_mul[c0 + j4 * 4]);
+          uint8_t* slot = rt + (c0 / 32) * 128 * 128 + row * 128 + ((j4 ^ sw) << 4);
+          const float4 mm = *reinterpret_cast<const float4*>(slot);
+          y[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + ad.x + mm.x;
+          y[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + ad.y + mm.y;
+          y[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + ad.z + mm.z;
+          y[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + ad.w + mm.w;
+          *reinterpret_cast<float4*>(slot) = make_float4(y[j4 * 4], y[j4 * 4 + 1], y[j4 * 4 + 2], y[j4 * 4 + 3]);
+        }
+        if (p.has_out_t) store_bf16_chunk(tt, y, c0);    // aliases A2: the chained MMA has completed (acc2_full)
+        if (p.stats_out != nullptr && fvalid) add_stats(y, c0);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      named_bar(1, 128);
+      if (elected) {
+        if (p.has_out_r)
+          for (int a = 0; a < C::RA; ++a) tma_store_3d(&p.tmR, rt + a * 128 * 128, a * 32, fl0, fb);
+        if (p.has_out_t)
+          for (int a = 0; a < C::TA; ++a) tma_store_3d(&p.tmT, tt + a * 128 * 128, a * 64, fl0, fb);
+        bulk_commit();
+        if (p.has_out_t) bulk_wait_read<0>();   // A2 (aliased output copy) is rewritten right after
+        else bulk_wait_read<1>();
+        if (use_r && fi > 0) mbar_arrive(&r_empty[(fi - 1) % NSR]);
+      }
+      if (p.has_out_t) named_bar(1, 128);       // everybody waits for the elected thread's wait_read before A2 is rewritten
+    };
     uint32_t i = 0;
     for (int t = t_begin; t < t_end; ++t, ++i) {
       const int b = t / p.tiles_per_clip;
@@ -443,6 +496,10 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
       const int s = i & 1;
       const int rs = i % NSR;
       const bool row_valid = l0 + row < p.L;
+      if (PIPE && pend && b != cur_b) {      // the pending tile belongs to the previous clip: finish it before its vectors go
+        finish_tile(p_b, p_l0, p_rs, p_valid, p_i);
+        pend = false;
+      }
       // (1) top-of-tile barrier: the elected thread has confirmed (bulk_wait_read) that earlier TMA stores no longer
       //     read the buffers this tile rewrites; per-clip epilogue vectors are rebuilt when the clip changes.
       if (b != cur_b) {
@@ -543,11 +600,37 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
             m[j4 * 4 + 3] = fmaf((__uint_as_float(v[j4 * 4 + 3]) + ad.w + x.w - mean) * rstd, gg.w, sh.w);
             *reinterpret_cast<float4*>(slot) = make_float4(m[j4 * 4], m[j4 * 4 + 1], m[j4 * 4 + 2], m[j4 * 4 + 3]);
           }
-          if (EPI == 2 || p.has_out_t) store_bf16_chunk(tt, m, c0);
+          if ((EPI == 2 && !PIPE) || (EPI != 2 && p.has_out_t)) store_bf16_chunk(tt, m, c0);
           if (EPI == 1 && p.stats_out != nullptr && row_valid) add_stats(m, c0);
         }
         tc_fence_before();
         mbar_arrive(&acc1_empty[s]);
+        if (PIPE) {
+          if (pend) finish_tile(p_b, p_l0, p_rs, p_valid, p_i);      // its chained MMA ran while this tile was normalised
+          // chained operand of THIS tile: bf16(m) from the fp32 slot + the onset context -> A2
+#pragma unroll
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            float m[32];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 mm = *reinterpret_cast<const float4*>(rt + (c0 / 32) * 128 * 128 + row * 128 + ((j4 ^ sw) << 4));
+              m[j4 * 4 + 0] = mm.x; m[j4 * 4 + 1] = mm.y; m[j4 * 4 + 2] = mm.z; m[j4 * 4 + 3] = mm.w;
+            }
+            store_bf16_chunk(sA2, m, c0);
+          }
+          {
+            const uint8_t* cx = sCTX + rs * C::CTX_BYTES + row * (p.ctx_ch * 2);
+            for (int j = 0; j < p.ctx_ch / 8; ++j) {
+              const int ch8 = (N % 64) / 8 + j;
+              *reinterpret_cast<uint4*>(sA2 + (N / 64) * 128 * 128 + row * 128 + ((ch8 ^ sw) << 4)) =
+                  *reinterpret_cast<const uint4*>(cx + j * 16);
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(a2_full);
+          pend = true; p_b = b; p_l0 = l0; p_rs = rs; p_valid = row_valid; p_i = i;
+          continue;                       // stores of this tile happen in finish_tile
+        }
         if (EPI == 2) {
           // onset context of this position -> K columns [N, N + ctx) of the chained operand
           {
@@ -600,6 +683,7 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
         if (use_r && i > 0) mbar_arrive(&r_empty[(i - 1) % NSR]);
       }
     }
+    if (PIPE && pend) finish_tile(p_b, p_l0, p_rs, p_valid, p_i);
     flush_stats(cur_b);
     if (elected) bulk_wait<0>();
   }
