@@ -5,9 +5,9 @@ Host-side mirror of the reference interface (``DiffusionModel.sample`` as called
 ``libsyncfusion_b200.so``.  PyTorch is used for device memory, streams and ``torch.distributed`` only.
 """
 from .config import UNetConfig  # noqa: F401
-from .model import DiffusionModel, UNetV0, VSampler, flat_param_name  # noqa: F401
+from .model import DiffusionModel, UNetV0, VSampler, flat_param_name, hydra_config, hydra_target  # noqa: F401
 from .synth import random_state_dict, synthetic_inputs  # noqa: F401
 from .parallel import shard_batch, gather_waveforms, sample_sharded  # noqa: F401
 
 __all__ = ["UNetConfig", "DiffusionModel", "UNetV0", "VSampler", "flat_param_name", "shard_batch",
-           "gather_waveforms", "sample_sharded"]
+           "gather_waveforms", "sample_sharded", "hydra_config", "hydra_target", "random_state_dict", "synthetic_inputs"]

@@ -287,3 +287,23 @@ class DiffusionModel:
         raise NotImplementedError("the VDiffusion training objective is out of scope of the B200 sampling path")
 
     __call__ = forward
+
+
+def hydra_config(net_t=None, diffusion_t=None, sampler_t=None, use_embedding_cfg: bool = True, precision: str = "bf16",
+                 upsample_mode: str = "nearest", **kw) -> UNetConfig:
+    """``UNetConfig`` from the keyword arguments Hydra passes for ``exp/model/diffusion.yaml:11-33`` (the partials
+    ``net_t`` / ``diffusion_t`` / ``sampler_t`` select upstream classes this package replaces and are ignored)."""
+    del net_t, diffusion_t, sampler_t
+    fields = {f for f in UNetConfig.__dataclass_fields__}
+    unknown = sorted(set(kw) - fields)
+    if unknown:
+        raise TypeError(f"unsupported DiffusionModel arguments for the B200 sampling path: {unknown}")
+    seq = ("channels", "factors", "items", "attentions", "cross_attentions", "context_channels")
+    kw = {k: (tuple(int(x) for x in v) if k in seq else v) for k, v in kw.items()}
+    return UNetConfig(use_embedding_cfg=bool(use_embedding_cfg), precision=precision, upsample_mode=upsample_mode, **kw)
+
+
+def hydra_target(device: "torch.device | str | int" = "cuda", **kw) -> DiffusionModel:
+    """Drop-in ``_target_`` for ``model.model`` of exp/model/diffusion.yaml."""
+    return DiffusionModel(hydra_config(**kw), device)
+

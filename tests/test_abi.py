@@ -77,3 +77,18 @@ def test_product_code_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_hydra_config_accepts_the_reference_yaml_keys():
+    """exp/model/diffusion.yaml:11-33 keyword set -> UNetConfig (the Hydra `_target_` swap of INTEGRATION.md)."""
+    import syncfusion_b200 as sf
+    cfg = sf.hydra_config(net_t=object(), diffusion_t=object(), sampler_t=object(), in_channels=1,
+                          channels=[8, 32, 64, 128, 256, 512, 1024, 1024], factors=[1, 4, 4, 4, 2, 2, 2, 2],
+                          items=[1, 2, 2, 2, 2, 2, 2, 4], attentions=[0, 0, 0, 0, 1, 1, 1, 1], attention_heads=8,
+                          attention_features=64, context_channels=[2, 8, 16, 32, 64, 128, 256, 256],
+                          use_embedding_cfg=True, embedding_max_length=1, embedding_features=512,
+                          cross_attentions=[1] * 8)
+    assert cfg == sf.UNetConfig()
+    with pytest.raises(TypeError):
+        sf.hydra_config(unknown_key=1)
+
