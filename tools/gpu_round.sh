@@ -15,9 +15,11 @@ opprof) timeout 600 python tools/op_profile.py > gpurun_out/op_profile.txt 2> gp
 ncusk) timeout 900 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats --section Occupancy --section SchedulerStats --clock-control none -k regex:sk_kernel -s 123 -c 123 -f -o gpurun_out/prof_sk python tools/ncu_step.py --steps 2 > gpurun_out/ncu_sk.log 2>&1; tail -n 2 gpurun_out/ncu_sk.log
   ncu -i gpurun_out/prof_sk.ncu-rep --page raw --csv > gpurun_out/prof_sk_raw.csv 2>/dev/null; rm -f gpurun_out/prof_sk.ncu-rep; ls -la gpurun_out;;
 timeline) timeout 600 python tools/sk_timeline.py --ops "${SK_OPS:-4:out,6:qkv,6:conv1,7:inject}" > gpurun_out/sk_timeline.txt 2>&1; tail -n 3 gpurun_out/sk_timeline.txt;;
-ncuone) # NCU_SKIP=<sk launch index> NCU_NAME=<tag>: one sk launch, full set + source
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:sk_kernel -s ${NCU_SKIP:-134} -c 1 -f -o gpurun_out/prof_${NCU_NAME:-sk_one} python tools/ncu_step.py --steps 2 > gpurun_out/ncu_${NCU_NAME:-sk_one}.log 2>&1; tail -n 1 gpurun_out/ncu_${NCU_NAME:-sk_one}.log; ls -la gpurun_out/*.ncu-rep;;
-ncutraffic) timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:sk_kernel -s 123 -c 123 --csv --log-file gpurun_out/sk_traffic.csv python tools/ncu_step.py --steps 2 > gpurun_out/ncu_traffic.log 2>&1; tail -n 2 gpurun_out/ncu_traffic.log;;
+ncuone) # NCU_SKIP=<launch index> NCU_NAME=<tag> NCU_KERNEL=<regex>: one launch, full set + source; only CSV exports travel back
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-sk_kernel} -s ${NCU_SKIP:-134} -c 1 -f -o gpurun_out/prof_${NCU_NAME:-sk_one} python tools/ncu_step.py --steps 2 > gpurun_out/ncu_${NCU_NAME:-sk_one}.log 2>&1; tail -n 1 gpurun_out/ncu_${NCU_NAME:-sk_one}.log
+  ncu -i gpurun_out/prof_${NCU_NAME:-sk_one}.ncu-rep --page details --csv > gpurun_out/ncu_full_${NCU_NAME:-sk_one}.csv 2>/dev/null
+  python tools/ncu_sass.py gpurun_out/prof_${NCU_NAME:-sk_one}.ncu-rep 40 > gpurun_out/ncu_sass_${NCU_NAME:-sk_one}.txt 2>&1
+  rm -f gpurun_out/prof_${NCU_NAME:-sk_one}.ncu-rep;;
 smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; tail -n 5 gpurun_out/smoke.log;;
 esac
 done
