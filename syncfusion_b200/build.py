@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-           "--use_fast_math" if False else "-DSFB_NO_FAST_MATH", *(["-DSFB_RK_NO_PIPE"] if os.environ.get("SFB_RK_NO_PIPE") else []), "-Xcompiler", "-fPIC", "-shared",
+           "--use_fast_math" if False else "-DSFB_NO_FAST_MATH", *(["-DSFB_RK_PIPE"] if os.environ.get("SFB_RK_PIPE") else []), "-Xcompiler", "-fPIC", "-shared",
            "-Xptxas", "-v" if verbose else "-O3", "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

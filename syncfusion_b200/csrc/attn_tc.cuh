@@ -183,13 +183,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
         for (int i = 0; i < BKV; ++i)
           if (i >= kv_valid) v[i] = 0xFF800000u;   // -inf
       }
-      float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]), mx2 = __uint_as_float(v[2]), mx3 = __uint_as_float(v[3]);
+      float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]);
 #pragma unroll
-      for (int i = 4; i < BKV; i += 4) {        // four independent chains: the max is a latency chain, not a throughput one
-        mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(v[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      for (int i = 2; i < BKV; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1])); }
+      const float mx = fmaxf(mx0, mx1);
       // lazy running max: rescale only when this row's max grew by more than 2^8 relative to the max in use
       const bool need = (mx - m_used) * sc > 8.f;             // true on the first tile (m_used = -inf)
       bool o_waited = false;
@@ -214,13 +211,13 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
         }
       }
       const float moff = m_used * sc;
-      float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-      // probabilities in place (fp32), row sum on the un-rounded values (four independent chains); the operand-precision
+      float rs0 = 0.f, rs1 = 0.f;
+      // probabilities in place (fp32), row sum on the un-rounded values (two independent chains); the operand-precision
       // rounding of P is zero-mean, so the normaliser differs from sum(round(P)) by ~1e-4 relative at most.
 #pragma unroll
       for (int i = 0; i < BKV; i += 2) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, -moff)), p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -moff));
-        if (i & 2) { rs2 += p0; rs3 += p1; } else { rs0 += p0; rs1 += p1; }
+        rs0 += p0; rs1 += p1;
         if constexpr (sizeof(T) == 2) {
           __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
           v[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);       // packed pair i/2 (slots below i are already consumed)
@@ -228,7 +225,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
           v[i] = __float_as_uint(from_f32<float>(p0)); v[i + 1] = __float_as_uint(from_f32<float>(p1));
         }
       }
-      l_run += (rs0 + rs1) + (rs2 + rs3);
+      l_run += rs0 + rs1;
       if (j > 0 && !o_waited) mbar_wait(o_full, (j - 1) & 1);   // P V(j-1) no longer reads the P tile
       // write this row's probabilities into the swizzled K-major P tile (operand precision)
       if constexpr (sizeof(T) == 2) {

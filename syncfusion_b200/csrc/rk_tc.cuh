@@ -439,10 +439,12 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
     // Software-pipelined chain (EPI == 2 with >= 4 residual stages): the second epilogue of tile i-1 (acc2 of the chained
     // inject MMA) runs AFTER the first epilogue of tile i, so the MMA round trip (a2_full -> issue -> commit -> acc2_full)
     // is covered by LayerNorm work instead of idling the only epilogue warpgroup (ncu: 72 % no-eligible cycles).
-#ifdef SFB_RK_NO_PIPE
-    constexpr bool PIPE = false;
-#else
+#ifdef SFB_RK_PIPE
     constexpr bool PIPE = EPI == 2 && C::NSR >= 4;      // depth 1 (five residual stages); depth 2 has only three
+#else
+    // Parity-green and 2.6 % faster on the depth-1 inject at N = 1, but the only 2-GPU run of a build that had it on
+    // hung (cause not established, GPU budget exhausted): off by default until a multi-GPU run clears it.
+    constexpr bool PIPE = false;
 #endif
     bool pend = false;
     int p_b = 0, p_l0 = 0, p_rs = 0;

@@ -40,7 +40,15 @@ def gather_waveforms(local: Tensor, batch: int, group: Optional[dist.ProcessGrou
     if local.shape[0] < cmax:
         pad = torch.cat([local, local.new_zeros((cmax - local.shape[0],) + tuple(local.shape[1:]))], dim=0)
     out = local.new_empty((world * cmax,) + tuple(local.shape[1:]))
+    # Host-side fence on both sides of the collective: the sampling kernels are persistent one-CTA-per-SM grids chained
+    # with programmatic dependent launch, and 2-GPU runs in which the NCCL kernel was enqueued straight behind / in front
+    # of them showed barrier-wait timeouts on rank 1 (open issue).  One sync per sample() is free
+    # next to ~0.4 s of sampling.
+    if local.is_cuda:
+        torch.cuda.current_stream(local.device).synchronize()
     dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    if local.is_cuda:
+        torch.cuda.current_stream(local.device).synchronize()
     if all(c == cmax for c in counts):
         return out
     return torch.cat([out[r * cmax: r * cmax + counts[r]] for r in range(world)], dim=0)
