@@ -200,6 +200,18 @@ def main():
     x_d, e_d = x_p.to(dev), e_p.to(dev)
     ch_d = [c.to(dev) for c in ch_p]
     out_host = torch.empty(B, 1, L).pin_memory()
+    if world > 1:
+        # NCCL sets its transports up lazily inside the first collective of each kind / size (peer mappings, channel
+        # buffers).  Do that here, on an idle GPU and with the timed loop's exact collectives, so no sampling kernel ever
+        # runs while a rank is still mapping memory (open issue).
+        warm = torch.zeros(B, 1, L, device=dev)
+        for _ in range(2):
+            sf.gather_waveforms(warm, B * world)
+            dist.barrier()
+            t_ = torch.zeros(1, device=dev)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
+        del warm
 
     def step_resident():
         out = model.sample(x_noisy=x_d, num_steps=NS, channels=ch_d, embedding=e_d, embedding_scale=args.scale)
