@@ -92,3 +92,20 @@ def test_hydra_config_accepts_the_reference_yaml_keys():
     with pytest.raises(TypeError):
         sf.hydra_config(unknown_key=1)
 
+
+def test_library_sass_has_tcgen05_tma_and_no_other_arch():
+    """The shipped .so is sm_100a-only machine code with tcgen05 MMAs (UTCHMMA), TMA loads / stores (UTMALDG / UTMASTG) and
+    TMEM loads (LDTM) - the mnemonics /opt/skills/guides/B200_PROFILING.md names as proof of the native path."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = str(_lib.LIB_PATH)
+    elf = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", elf))
+    assert archs == {"100a"}, archs
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True).stdout      # ~10 s
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
