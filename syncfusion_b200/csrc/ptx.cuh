@@ -57,10 +57,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a mis-programmed pipeline traps (-> launch error the host reports) instead of hanging the GPU.
-// The bound is 2^24 polls of the hinted try_wait below: a healthy wait lasts less than a kernel (< 1 ms: a few hundred
-// parked polls of ~4 us, at most ~30 k woken ones), 2^24 polls are 0.5 s (woken) to 67 s (parked).  An un-hinted 2^26 bound
-// fired on rank 1 of 2-GPU runs (clip-sharded sample() + NCCL all-gather, 50 steps) and one 2-GPU run with a 2^31 bound
-// hung: see DESIGN.md section 6, open issue.  The loop body must stay exactly this small: timer reads, a diagnostic record or an
+// The bound is 2^28 polls of the hinted try_wait below.  A healthy wait lasts less than a tile (< 1 ms: a few hundred
+// parked polls of ~4 us, at most ~60 k woken ones); 2^28 polls are 4-9 s of continuously woken polling or 18 min of
+// parked polling, so a transient multi-second stall survives and a true deadlock still ends in a launch error.  An
+// un-hinted 2^26 bound fired on rank 1 of 2-GPU runs (clip-sharded sample() + NCCL all-gather, 50 steps) and one 2-GPU
+// run with a 2^31 bound hung: see DESIGN.md section 6, open issue.  The loop body must stay exactly this small: timer reads, a diagnostic record or an
 // out-of-line slow path at the ~25 wait sites of the 128-register kernels each made the whole sampling step 2-5 %
 // slower (A/B measured on the same box: 385 ms vs 394-406 ms per 16-clip step).
 // try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes or ~1 ms
@@ -95,7 +96,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 #else
   while (!mbar_try_wait_hint(bar, parity)) {
-    if (++spins > (1u << 24)) { __trap(); }
+    if (++spins > (1u << 28)) { __trap(); }
   }
 #endif
 }
