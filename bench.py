@@ -185,6 +185,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # connect every NCCL transport inside init_process_group instead of lazily inside the first collectives: no
+        # peer / VMM mapping work is left for the time the sampling kernels run (open issue)
+        os.environ.setdefault("NCCL_RUNTIME_CONNECT", "0")
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
     B, L, NS = args.batch, args.length, args.sample_steps
