@@ -102,6 +102,16 @@ int sfb_dbg_set_op_limit(sfb_handle* h, int n_ops);
  * "kind depth stack item out_offset out_bytes rows cols dtype". */
 int sfb_dbg_plan_size(sfb_handle* h, int64_t B, int64_t L, int cfg_on, void* workspace, size_t workspace_bytes);
 int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len);
+/* Post-mortem of a device barrier-wait timeout.  Every mbarrier wait of the tcgen05 / TMA pipelines is bounded
+ * (about 8 s when nothing arrives); a waiter that hits the bound records {kernel source line, plan op, CTA, thread,
+ * barrier, parity, raw barrier word} in a host-mapped log and traps, so the launch ends in a CUDA error instead of a
+ * hung GPU.  Copies the decoded log into buf (NUL terminated, truncated to buf_len) and returns its full length,
+ * 0 if no wait ever timed out.  Readable after the CUDA context is lost.  sfb_last_error() appends the same text to
+ * any SFB_ERR_CUDA message. */
+int sfb_dbg_wait_log(sfb_handle* h, char* buf, int buf_len);
+/* Test hook for the above: launches one warp that waits on a barrier nobody arrives on and synchronises the stream;
+ * returns SFB_ERR_CUDA with the decoded log in sfb_last_error().  The CUDA context is lost afterwards. */
+int sfb_dbg_fault_inject(sfb_handle* h, void* stream);
 /* Per-op device timing: when enabled, every launch of a U-Net evaluation is bracketed by CUDA events on the caller's
  * stream; after the caller synchronises, the report holds one line per plan op of the most recent evaluation:
  * "index kind depth stack item ms flops bytes" (algorithmic flops / bytes).  bench.py's roofline comes from this. */

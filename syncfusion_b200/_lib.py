@@ -13,7 +13,7 @@ SFB_MAX_DEPTH = 16
 EXPORTS = [
     "sfb_create", "sfb_destroy", "sfb_last_error", "sfb_set_param", "sfb_finalize", "sfb_workspace_bytes",
     "sfb_unet_forward", "sfb_sample", "sfb_last_launch_count", "sfb_dbg_set_op_limit", "sfb_dbg_plan_size",
-    "sfb_dbg_op_info", "sfb_dbg_sk_timeline", "sfb_dbg_profile", "sfb_dbg_profile_report", "sfb_dbg_gemm", "sfb_dbg_attention",
+    "sfb_dbg_op_info", "sfb_dbg_wait_log", "sfb_dbg_fault_inject", "sfb_dbg_sk_timeline", "sfb_dbg_profile", "sfb_dbg_profile_report", "sfb_dbg_gemm", "sfb_dbg_attention",
 ]
 
 
@@ -63,11 +63,16 @@ def load() -> C.CDLL:
     lib.sfb_dbg_plan_size.argtypes = [vp, i64, i64, i32, vp, C.c_size_t]
     lib.sfb_dbg_op_info.argtypes = [vp, i32, C.c_char_p, i32]
     lib.sfb_dbg_sk_timeline.argtypes = [vp, i32, vp, i32]
+    if not (os.environ.get("SFB_LIB") and not hasattr(lib, "sfb_dbg_wait_log")):   # an older A/B build may lack these two
+        lib.sfb_dbg_wait_log.argtypes = [vp, C.c_char_p, i32]
+        lib.sfb_dbg_fault_inject.argtypes = [vp, vp]
     lib.sfb_dbg_profile.argtypes = [vp, i32]
     lib.sfb_dbg_profile_report.argtypes = [vp, C.c_char_p, i32]
     lib.sfb_dbg_gemm.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.sfb_dbg_attention.argtypes = [i32, vp, vp, i32, i32, vp]
     for name in EXPORTS:          # every symbol the header declares must resolve
+        if os.environ.get("SFB_LIB") and name in ("sfb_dbg_wait_log", "sfb_dbg_fault_inject") and not hasattr(lib, name):
+            continue
         getattr(lib, name)
     _lib = lib
     return lib

@@ -10,7 +10,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libsyncfusion_b200.so"
 SOURCES = ["sfb.cu"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "attn_tc.cuh", "elementwise.cuh", "d0.cuh", "prepare.cuh", "rk_tc.cuh", "sk_tc.cuh", "sk2_tc.cuh"]
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "attn_tc.cuh", "elementwise.cuh", "d0.cuh", "prepare.cuh", "rk_tc.cuh", "sk_tc.cuh"]
 
 
 def _nvcc() -> str:

@@ -13,6 +13,8 @@
 // multiply of the accumulator.  The [B, 8, N, N] score matrix the reference materialises never exists.
 #pragma once
 #include "ptx.cuh"
+#undef SFB_FILE_ID
+#define SFB_FILE_ID 2   // attn_tc.cuh
 
 namespace sfb {
 
@@ -24,6 +26,7 @@ struct AttnParams {
   T* out;             // [B, N, 512]
   int n_tokens;
   float scale_log2;   // log2(e) / sqrt(64)
+  int tag;            // plan op index (wait log)
 };
 
 template <typename T> struct AttnCfg;

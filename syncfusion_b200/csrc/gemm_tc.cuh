@@ -18,6 +18,8 @@
 //                  squares per (clip, group)) of the OUTPUT, so no separate statistics pass over HBM is ever made.
 #pragma once
 #include "ptx.cuh"
+#undef SFB_FILE_ID
+#define SFB_FILE_ID 1   // gemm_tc.cuh (wait-log call sites, ptx.cuh)
 
 namespace sfb {
 
@@ -48,6 +50,7 @@ struct GemmParams {
   double* stats;          // [B, 8, 2] or null
   int n_tiles;            // N / BN
   int total_tiles;        // B * tiles_per_clip * n_tiles
+  int tag;                // plan op index (wait log)
 };
 
 constexpr int kGemmBM = 128;

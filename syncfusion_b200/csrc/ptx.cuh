@@ -56,18 +56,53 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a mis-programmed pipeline traps (-> launch error the host reports) instead of hanging the GPU.
-// The bound is 2^28 polls of the hinted try_wait below.  A healthy wait lasts less than a tile (< 1 ms: a few hundred
-// parked polls of ~4 us, at most ~60 k woken ones); 2^28 polls are 4-9 s of continuously woken polling or 18 min of
-// parked polling, so a transient multi-second stall survives and a true deadlock still ends in a launch error.  An
-// un-hinted 2^26 bound fired on rank 1 of 2-GPU runs (clip-sharded sample() + NCCL all-gather, 50 steps) and one 2-GPU
-// run with a 2^31 bound hung: see DESIGN.md section 6, open issue.  The loop body must stay exactly this small: timer reads, a diagnostic record or an
-// out-of-line slow path at the ~25 wait sites of the 128-register kernels each made the whole sampling step 2-5 %
-// slower (A/B measured on the same box: 385 ms vs 394-406 ms per 16-clip step).
-// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes or ~1 ms
-// passed, so a waiting warp issues almost nothing (it does not compete with the working warps of its sub-partition) and
-// a poll parks for ~4 us on B200 whatever the hint says (tools/trywait_bench.cu), less when arrivals / TMA byte counts
-// keep waking the waiter.
+// Bounded wait with a post-mortem record.  A waiter polls the hinted try_wait below; when the poll count passes
+// c_wait_bound (2^21: >= 30 ms of continuously woken polling - 30x any healthy wait of these kernels - or ~8 s of
+// parked polling, a parked poll lasts ~4 us on B200, tools/trywait_bench.cu) lane 0 of the warp writes ONE record
+// {call site, barrier address, parity, CTA, thread, op tag, raw barrier word} into a host-mapped log, keeps polling
+// for another 2^17 polls so that the other stuck roles of the grid get their records in, and traps.  The host
+// (sfb.cu: wait_log_text) decodes the log into sfb_last_error(): a pipeline bug ends in seconds with the kernel, the
+// role and the barrier named, instead of a hung GPU.  The hot loop stays {try_wait, add, compare, branch}: everything
+// else is in the cold block (measured in r1: any extra instruction in the loop costs 2-5 % of the whole step).
+struct WaitRecord { uint32_t site, bar, cta_x, cta_yz, thread, tag, state_lo, state_hi; };
+constexpr int kWaitRecMax = 96;
+constexpr int kWaitDumpWords = 96;
+struct WaitLog {
+  uint32_t count, dump_base, dump_words, smem_bytes;
+  WaitRecord rec[kWaitRecMax];
+  uint64_t dump[kWaitDumpWords];      // raw shared-memory words around the first reporter's barrier (all barriers of its CTA)
+};
+__device__ WaitLog* g_wait_log = nullptr;            // device pointer of the host-mapped log (sfb_create)
+__constant__ uint32_t c_wait_bound = 1u << 21;       // SFB_WAIT_BOUND_LOG2 overrides (compute-sanitizer runs)
+
+__device__ __noinline__ void wait_timeout_report(uint32_t bar, uint32_t parity, uint32_t site, uint32_t tag) {
+  WaitLog* lg = g_wait_log;
+  if (lg == nullptr) return;
+  const uint32_t slot = atomicAdd(&lg->count, 1u);
+  if (slot >= (uint32_t)kWaitRecMax) return;
+  uint64_t st;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(st) : "r"(bar));
+  WaitRecord r;
+  r.site = site; r.bar = bar | (parity << 31); r.cta_x = blockIdx.x; r.cta_yz = blockIdx.y | (blockIdx.z << 16);
+  r.thread = threadIdx.x | (blockDim.x << 16); r.tag = tag; r.state_lo = (uint32_t)st; r.state_hi = (uint32_t)(st >> 32);
+  lg->rec[slot] = r;
+  if (slot == 0) {
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    const uint32_t lo = bar >= 384u ? ((bar - 384u) & ~7u) : 0u;
+    uint32_t n = 0;
+    for (; n < (uint32_t)kWaitDumpWords && lo + 8u * n + 8u <= dyn; ++n) {
+      uint64_t w;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(lo + 8u * n));
+      lg->dump[n] = w;
+    }
+    lg->dump_base = lo; lg->dump_words = n; lg->smem_bytes = dyn;
+  }
+  __threadfence_system();
+}
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes or the
+// hint elapses, so a waiting warp issues almost nothing (it does not compete with the working warps of its
+// sub-partition).
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -81,25 +116,18 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, uint32_t site, uint32_t tag) {
   uint32_t spins = 0;
-#ifdef SFB_WAIT_DEBUG      // diagnostic build: report waits that outlast 2^26 polls instead of trapping
-  unsigned long long t0 = 0;
   while (!mbar_try_wait_hint(bar, parity)) {
-    if (spins == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    if (++spins == (1u << 26)) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      printf("[sfb long wait] 2^26 polls in %.3f s: block (%d,%d,%d)/%d thread %d/%d bar 0x%x parity %u\n", (t1 - t0) * 1e-9, blockIdx.x,
-             blockIdx.y, blockIdx.z, gridDim.x, threadIdx.x, blockDim.x, smem_u32(bar), parity);
+    if (++spins >= c_wait_bound) {
+      if (spins == c_wait_bound) { if (lane_id() == 0) wait_timeout_report(smem_u32(bar), parity, site, tag); }
+      else if (spins - c_wait_bound > (1u << 17)) { __threadfence_system(); __trap(); }
     }
   }
-#else
-  while (!mbar_try_wait_hint(bar, parity)) {
-    if (++spins > (1u << 28)) { __trap(); }
-  }
-#endif
 }
+// Call-site form: `p` is the kernel's __grid_constant__ parameter struct (its `tag` = plan op index lives in the
+// constant bank, so naming the op costs no register), SFB_FILE_ID is set by each kernel header.
+#define mbar_wait(bar, parity) ::sfb::mbar_wait_at((bar), (parity), (uint32_t)((SFB_FILE_ID << 16) | __LINE__), (uint32_t)p.tag)
 
 // ------------------------------------------------------------------ programmatic dependent launch (PDL)
 // Every kernel of the per-step chain calls pdl_trigger() first (the NEXT kernel's CTAs may be scheduled as soon as

@@ -20,6 +20,8 @@
 // Instantiations (bf16 mode): ResNet conv1 (R1), ResNet conv2 + Modulation + Inject chain (R2), patchify Down, Up.
 #pragma once
 #include "ptx.cuh"
+#undef SFB_FILE_ID
+#define SFB_FILE_ID 3   // rk_tc.cuh
 
 namespace sfb {
 
@@ -42,6 +44,7 @@ struct RkParams {
   int L, tiles_per_clip, total_tiles, ctx_bmod, ctx_ch;
   int has_resid, has_out_r, has_out_t;
   float eps;
+  int tag;                  // plan op index (wait log)
 };
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {

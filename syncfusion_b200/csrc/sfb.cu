@@ -22,9 +22,6 @@
 #include "prepare.cuh"
 #include "rk_tc.cuh"
 #include "sk_tc.cuh"
-#ifdef SFB_ENABLE_SK2   // experimental CTA-pair variant (slower than the single-CTA kernel as of r1; not built by default)
-#include "sk2_tc.cuh"
-#endif
 
 using namespace sfb;
 
@@ -137,6 +134,34 @@ struct DepthW {
 enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN, OP_RK, OP_SK, OP_D0_CONV1, OP_D0_TAIL };
 const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn", "rk", "sk", "d0_conv1", "d0_tail"};
 
+// ------------------------------------------------------------------------------------------------ wait log (ptx.cuh)
+// One host-mapped log per process: the device writes it when a barrier wait outlasts c_wait_bound (then traps); the
+// host can still read it after the context is lost.
+WaitLog* g_wait_log_host = nullptr;
+int wait_log_init() {
+  if (g_wait_log_host) return 0;
+  void* h = nullptr;
+  if (cudaHostAlloc(&h, sizeof(WaitLog), cudaHostAllocMapped) != cudaSuccess) return -1;
+  memset(h, 0, sizeof(WaitLog));
+  void* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return -1;
+  WaitLog* dp = reinterpret_cast<WaitLog*>(d);
+  if (cudaMemcpyToSymbol(g_wait_log, &dp, sizeof dp) != cudaSuccess) return -1;
+  if (const char* e = getenv("SFB_WAIT_BOUND_LOG2")) {
+    int lg = atoi(e);
+    if (lg >= 10 && lg <= 31) {
+      uint32_t v = 1u << lg;
+      if (cudaMemcpyToSymbol(c_wait_bound, &v, sizeof v) != cudaSuccess) return -1;
+    }
+  }
+  g_wait_log_host = reinterpret_cast<WaitLog*>(h);
+  return 0;
+}
+const char* wait_site_file(uint32_t id) {
+  switch (id) { case 9: return "sfb.cu"; case 1: return "gemm_tc.cuh"; case 2: return "attn_tc.cuh"; case 3: return "rk_tc.cuh"; case 4: return "sk_tc.cuh"; }
+  return "?";
+}
+
 struct EngineBase {
   sfb_unet_config cfg;
   int device = 0;
@@ -159,6 +184,33 @@ struct EngineBase {
   virtual int profile_report(char* buf, int len) = 0;
   virtual int sk_timeline(int op_index, long long* host_buf, int n) { (void)op_index; (void)host_buf; (void)n; return SFB_ERR_UNSUPPORTED; }
   bool profiling = false;
+  virtual std::string describe_wait(const WaitRecord& r) { (void)r; return ""; }
+  // Text of the device wait log ("" if no wait timed out): one line per stuck waiter + the raw barrier words.
+  std::string wait_log_text() {
+    const WaitLog* lg = g_wait_log_host;
+    if (!lg || lg->count == 0) return "";
+    char b[512];
+    std::string out;
+    const uint32_t n = std::min<uint32_t>(lg->count, kWaitRecMax);
+    snprintf(b, sizeof b, "barrier wait timed out: %u waiter(s) reported (first %u shown)\n", lg->count, n);
+    out += b;
+    for (uint32_t i = 0; i < n; ++i) {
+      const WaitRecord& r = lg->rec[i];
+      snprintf(b, sizeof b, "  [%u] %s:%u op#%u cta(%u,%u,%u) thread %u/%u (warp %u) bar@0x%x parity %u state 0x%08x%08x %s\n", i,
+               wait_site_file(r.site >> 16), r.site & 0xFFFFu, r.tag, r.cta_x, r.cta_yz & 0xFFFFu, r.cta_yz >> 16, r.thread & 0xFFFFu,
+               r.thread >> 16, (r.thread & 0xFFFFu) >> 5, r.bar & 0x7FFFFFFFu, r.bar >> 31, r.state_hi, r.state_lo, describe_wait(r).c_str());
+      out += b;
+    }
+    snprintf(b, sizeof b, "  shared-memory words from 0x%x (%u x 8 B, dynamic smem %u B) of cta(%u,...) of record 0:\n   ", lg->dump_base,
+             lg->dump_words, lg->smem_bytes, lg->rec[0].cta_x);
+    out += b;
+    for (uint32_t i = 0; i < lg->dump_words && i < (uint32_t)kWaitDumpWords; ++i) {
+      snprintf(b, sizeof b, " %016llx%s", (unsigned long long)lg->dump[i], (i % 8 == 7) ? "\n   " : "");
+      out += b;
+    }
+    out += "\n";
+    return out;
+  }
   int fail(int code, const char* fmt, ...) {
     char b[512];
     va_list ap;
@@ -166,6 +218,7 @@ struct EngineBase {
     vsnprintf(b, sizeof b, fmt, ap);
     va_end(ap);
     err = b;
+    if (code == SFB_ERR_CUDA) { const std::string w = wait_log_text(); if (!w.empty()) err += "\n" + w; }
     return code;
   }
 };
@@ -258,11 +311,6 @@ struct Engine : EngineBase {
   bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aids: force the unfused generic path
   bool no_sk = getenv("SFB_NO_SK") != nullptr;
   bool no_d0_fused = getenv("SFB_NO_D0_FUSED") != nullptr;
-#ifdef SFB_ENABLE_SK2
-  bool no_sk2 = getenv("SFB_SK2") == nullptr;     // SFB_SK2=1: CTA-pair streaming-K kernel (sk2_tc.cuh) instead of the single-CTA one
-#else
-  bool no_sk2 = true;
-#endif
 
   struct Op {
     int kind = 0, depth = 0, stack = 0, item = 0;
@@ -380,9 +428,6 @@ struct Engine : EngineBase {
     if (set_kernel_attrs<T>() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (kBF16 && rk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (rk) failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (kBF16 && sk_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (sk) failed: %s", cudaGetErrorString(cudaGetLastError()));
-#ifdef SFB_ENABLE_SK2
-    if (kBF16 && sk2_set_attrs() != cudaSuccess) return fail(SFB_ERR_CUDA, "cudaFuncSetAttribute (sk2) failed: %s", cudaGetErrorString(cudaGetLastError()));
-#endif
 
     // time conditioning (A.3)
     t_w = upload_f(get("time.weights", {128}));
@@ -763,7 +808,7 @@ struct Engine : EngineBase {
     if (g.K2 > 0) { if (!make_tmap3<__nv_bfloat16>(&p.tmA2, a2, g.K2, L, B2, 64, 128)) return false; }
     else p.tmA2 = p.tmA1;
     if (!make_tmap3<__nv_bfloat16>(&p.tmW, w_override ? w_override : g.w, (uint64_t)(g.K1 + g.K2), (uint64_t)g.taps * g.N,
-                                   (uint64_t)w_copies, 64, no_sk2 ? BN : BN / 2)) return false;
+                                   (uint64_t)w_copies, 64, BN)) return false;
     p.w_bmod = 1;
     p.tmR = p.tmA1; p.tmRs = p.tmA1; p.tmT = p.tmA1;
     p.L = L; p.tiles_per_clip = (L + 127) / 128; p.N = g.N; p.n_tiles = g.N / BN;
@@ -1207,6 +1252,51 @@ struct Engine : EngineBase {
     return SFB_OK;
   }
 
+  // Names the op and the barrier of a wait-log record (barrier arrays as laid out in sk_tc.cuh / rk_tc.cuh / attn_tc.cuh).
+  std::string describe_wait(const WaitRecord& r) override {
+    if (r.tag >= plan.ops.size()) return "";
+    const Op& o = plan.ops[r.tag];
+    char b[256];
+    snprintf(b, sizeof b, "| %s d%d s%d i%d '%s' B=%d L=%d C=%d", kOpNames[o.kind], o.depth, o.stack, o.item, o.ck, o.B, o.L, o.C);
+    std::string out = b;
+    const uint32_t addr = r.bar & 0x7FFFFFFFu;
+    auto name_of = [&](uint32_t bars_off, const char* const* names, const int* counts, int n) {
+      const uint32_t idx = ((addr - bars_off) & 1023u) / 8;     // dynamic shared memory starts 1024-aligned
+      uint32_t k = idx;
+      for (int j = 0; j < n; ++j) {
+        if (k < (uint32_t)counts[j]) { snprintf(b, sizeof b, " bar=%s[%u]", names[j], k); out += b; return; }
+        k -= counts[j];
+      }
+      snprintf(b, sizeof b, " bar=#%u", idx); out += b;
+    };
+    if (o.kind == OP_SK) {
+      const SkParams& q = o.sp;
+      const uint32_t fixed = o.BN == 256 ? SkCfg<256>::fixed_bytes(q.epi12) - SkCfg<256>::BAR_BYTES : SkCfg<128>::fixed_bytes(q.epi12) - SkCfg<128>::BAR_BYTES;
+      const uint32_t off = q.na * SkCfg<128>::A_BYTES + q.nb * o.BN * 128 + q.nr * SkCfg<128>::R_BYTES + fixed;
+      static const char* const names[] = {"a_full", "a_empty", "op_full", "b_full", "b_empty", "acc_full", "acc_empty", "rc_full", "rc_empty"};
+      static const int counts[] = {4, 4, 4, 6, 6, 2, 2, 6, 6};
+      snprintf(b, sizeof b, " BN=%d taps=%d xf=%d epi12=%d na/nb/nr=%d/%d/%d resid=%d k1c=%d k2c=%d tiles=%d", o.BN, q.taps, q.xf, q.epi12, q.na, q.nb,
+               q.nr, q.resid_mode, q.k1_chunks, q.k2_chunks, q.total_tiles);
+      out += b;
+      name_of(off, names, counts, 9);
+    } else if (o.kind == OP_RK) {
+      uint32_t off = 0;
+      int idn = 0;
+#define X(a, b_, c, d, e_, f, g) if (o.rk_id == idn++) off = RkCfg<a, b_, c, d, e_, f, g>::OFF_BAR;
+      SFB_RK_LIST(X)
+#undef X
+      static const char* const names[] = {"w_full", "a_full", "a_empty", "op_full", "acc1_full", "acc1_empty", "a2_full", "acc2_full", "r_full", "r_empty"};
+      static const int counts[] = {1, 4, 4, 4, 2, 2, 1, 1, 5, 5};
+      snprintf(b, sizeof b, " rk_id=%d tiles=%d", o.rk_id, o.rp.total_tiles); out += b;
+      name_of(off, names, counts, 10);
+    } else if (o.kind == OP_ATTN) {
+      static const char* const names[] = {"q_full", "kv_full", "kv_empty", "s_full", "p_ready", "o_full", "s_free"};
+      static const int counts[] = {1, 2, 2, 1, 1, 1, 1};
+      name_of((uint32_t)attn_smem_bytes<T>() - 256, names, counts, 7);
+    }
+    return out;
+  }
+
   int ensure_plan(int64_t B, int64_t L, int cfg_on, int64_t rows, void* ws, size_t ws_bytes) {
     if (!finalized) return fail(SFB_ERR_STATE, "finalize first");
     size_t need = 0;
@@ -1226,6 +1316,10 @@ struct Engine : EngineBase {
     fold_items.clear(); fold_next = 0; fold_rows = 0;
     rc = build_block(0);
     if (rc) { plan.ops.clear(); return rc; }
+    for (size_t i = 0; i < plan.ops.size(); ++i) {      // plan index of every op, reported by the device wait log (ptx.cuh)
+      Op& o = plan.ops[i];
+      o.sp.tag = o.rp.tag = o.ap.tag = o.gp.tag = (int)i;
+    }
     if constexpr (kBF16) {      // shared-memory ring depths / epilogue width of every streaming-K op (sk_tc.cuh)
       const bool no_epi12 = getenv("SFB_NO_EPI12") != nullptr;
       for (Op& o : plan.ops) {
@@ -1378,9 +1472,6 @@ struct Engine : EngineBase {
               else { p.colscale = sc.frow + o.ft_off; p.cs_bstride = sc.bstride; p.cs_bmod = sc.bmod; }
             }
             const int epi = sk_epi_of(p.ln_fold, p.resid_mode, p.colscale != nullptr);
-#ifdef SFB_ENABLE_SK2
-            if (!no_sk2) { sk2_launch(o.sk_id, p, num_sms(), st); break; }
-#endif
             sk_launch(o.sk_id, epi, p, num_sms(), st);
           }
           break;
@@ -1516,6 +1607,17 @@ struct Engine : EngineBase {
 
 }  // namespace
 
+// Fault injection for the wait log: one warp waits on a barrier nobody ever arrives on (tests/test_gpu_waitlog.py).
+struct FaultParams { int tag; };
+#undef SFB_FILE_ID
+#define SFB_FILE_ID 9
+__global__ void wait_fault_kernel(const __grid_constant__ FaultParams p) {
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+}
+
 // ================================================================================================== C ABI
 struct sfb_handle {
   std::unique_ptr<EngineBase> e;
@@ -1561,6 +1663,7 @@ int sfb_create(const sfb_unet_config* cfg, int device, sfb_handle** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SFB_ERR_CUDA;
   if (prop.major != 10) return SFB_ERR_UNSUPPORTED;   // tcgen05 / TMEM kernels are sm_100a only
+  if (wait_log_init() != 0) return SFB_ERR_CUDA;
   sfb_handle* h = new sfb_handle();
   if (cfg->precision == SFB_PRECISION_BF16) h->e.reset(new Engine<__nv_bfloat16>());
   else h->e.reset(new Engine<float>());
@@ -1605,6 +1708,7 @@ int sfb_unet_forward(sfb_handle* h, const float* x, const float* sigma, const fl
                      void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return SFB_ERR_INVALID;
   if (!x || !sigma || !channels || !v_out) return h->e->fail(SFB_ERR_INVALID, "null argument");
+  if (cudaSetDevice(h->e->device) != cudaSuccess) return h->e->fail(SFB_ERR_CUDA, "cudaSetDevice(%d) failed", h->e->device);
   return h->e->unet_forward(x, sigma, channels, n_channels, embedding, M, embedding_scale, v_out, B, L, workspace,
                             workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -1614,6 +1718,7 @@ int sfb_sample(sfb_handle* h, const float* x_noisy, int num_steps, const float* 
                const float* teacher_x, int64_t B, int64_t L, void* workspace, size_t workspace_bytes, void* stream) {
   if (!h) return SFB_ERR_INVALID;
   if (!x_noisy || !channels || !x_out) return h->e->fail(SFB_ERR_INVALID, "null argument");
+  if (cudaSetDevice(h->e->device) != cudaSuccess) return h->e->fail(SFB_ERR_CUDA, "cudaSetDevice(%d) failed", h->e->device);
   return h->e->sample(x_noisy, num_steps, channels, n_channels, embedding, M, embedding_scale, x_out, traj_x, traj_v,
                       teacher_x, B, L, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
@@ -1641,6 +1746,20 @@ int sfb_dbg_profile_report(sfb_handle* h, char* buf, int buf_len) {
 int sfb_dbg_sk_timeline(sfb_handle* h, int op_index, long long* host_buf, int n) {
   if (!h) return SFB_ERR_INVALID;
   return h->e->sk_timeline(op_index, host_buf, n);
+}
+int sfb_dbg_wait_log(sfb_handle* h, char* buf, int buf_len) {
+  if (!h || !buf || buf_len <= 0) return SFB_ERR_INVALID;
+  const std::string w = h->e->wait_log_text();
+  snprintf(buf, (size_t)buf_len, "%s", w.c_str());
+  return (int)w.size();
+}
+int sfb_dbg_fault_inject(sfb_handle* h, void* stream) {
+  if (!h) return SFB_ERR_INVALID;
+  FaultParams fp{12345};
+  wait_fault_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(fp);
+  cudaError_t e = cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return h->e->fail(SFB_ERR_CUDA, "fault injection: %s", cudaGetErrorString(e));
+  return SFB_OK;
 }
 int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len) {
   if (!h || !buf) return SFB_ERR_INVALID;

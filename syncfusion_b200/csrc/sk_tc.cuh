@@ -18,6 +18,8 @@
 //               IN PLACE over the residual chunk + bf16 chunk -> TMA stores; output statistics on the fly.
 #pragma once
 #include "rk_tc.cuh"
+#undef SFB_FILE_ID
+#define SFB_FILE_ID 4   // sk_tc.cuh
 
 namespace sfb {
 
@@ -58,6 +60,7 @@ struct SkParams {
   // shared-memory ring depths of this op (host: sk_pick_rings) and the epilogue width
   int na, nb, nr;               // A / weight / residual stages
   int epi12;                    // xf == 0 ops: the four idle A-transform warps join the epilogue (12 warps, three chunk groups)
+  int tag;                      // plan op index (wait log)
   long long* dbg;               // optional timeline buffer (CTA 0 only): [role][256] clock64 stamps (tools/sk_timeline.py)
 };
 

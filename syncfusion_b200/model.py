@@ -234,6 +234,14 @@ class UNetV0:
                              flops=float(flops), bytes=float(nbytes)))
         return rows
 
+    def wait_log(self) -> str:
+        """Decoded device barrier-wait timeout log ('' if none); readable even after the CUDA context is lost."""
+        if not hasattr(self._lib, "sfb_dbg_wait_log"):
+            return ""
+        buf = C.create_string_buffer(1 << 16)
+        self._lib.sfb_dbg_wait_log(self._h, buf, len(buf))
+        return buf.value.decode(errors="replace")
+
     def debug_set_op_limit(self, n: int):
         self._check(self._lib.sfb_dbg_set_op_limit(self._h, int(n)))
 
