@@ -65,39 +65,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // role and the barrier named, instead of a hung GPU.  The hot loop stays {try_wait, add, compare, branch}: everything
 // else is in the cold block (measured in r1: any extra instruction in the loop costs 2-5 % of the whole step).
 struct WaitRecord { uint32_t site, bar, cta_x, cta_yz, thread, tag, state_lo, state_hi; };
-constexpr int kWaitRecMax = 96;
-constexpr int kWaitDumpWords = 96;
+constexpr int kWaitRecMax = 120;
 struct WaitLog {
-  uint32_t count, dump_base, dump_words, smem_bytes;
+  uint32_t count, pad[7];
   WaitRecord rec[kWaitRecMax];
-  uint64_t dump[kWaitDumpWords];      // raw shared-memory words around the first reporter's barrier (all barriers of its CTA)
 };
 __device__ WaitLog* g_wait_log = nullptr;            // device pointer of the host-mapped log (sfb_create)
 __constant__ uint32_t c_wait_bound = 1u << 21;       // SFB_WAIT_BOUND_LOG2 overrides (compute-sanitizer runs)
 
-__device__ __noinline__ void wait_timeout_report(uint32_t bar, uint32_t parity, uint32_t site, uint32_t tag) {
+// Inlined on purpose: as a __noinline__ call the ABI's register constraints made the 168-register attention kernel
+// spill (+11 % on that kernel); inlined, the cold block needs a handful of scratch registers at the wait site only.
+__device__ __forceinline__ void wait_timeout_report(uint32_t bar, uint32_t parity, uint32_t site, uint32_t tag) {
   WaitLog* lg = g_wait_log;
   if (lg == nullptr) return;
   const uint32_t slot = atomicAdd(&lg->count, 1u);
   if (slot >= (uint32_t)kWaitRecMax) return;
-  uint64_t st;
-  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(st) : "r"(bar));
-  WaitRecord r;
-  r.site = site; r.bar = bar | (parity << 31); r.cta_x = blockIdx.x; r.cta_yz = blockIdx.y | (blockIdx.z << 16);
-  r.thread = threadIdx.x | (blockDim.x << 16); r.tag = tag; r.state_lo = (uint32_t)st; r.state_hi = (uint32_t)(st >> 32);
-  lg->rec[slot] = r;
-  if (slot == 0) {
-    uint32_t dyn;
-    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    const uint32_t lo = bar >= 384u ? ((bar - 384u) & ~7u) : 0u;
-    uint32_t n = 0;
-    for (; n < (uint32_t)kWaitDumpWords && lo + 8u * n + 8u <= dyn; ++n) {
-      uint64_t w;
-      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(lo + 8u * n));
-      lg->dump[n] = w;
-    }
-    lg->dump_base = lo; lg->dump_words = n; lg->smem_bytes = dyn;
-  }
+  uint32_t lo, hi;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(bar));
+  volatile uint32_t* r = reinterpret_cast<volatile uint32_t*>(&lg->rec[slot]);
+  r[0] = site; r[1] = bar | (parity << 31); r[2] = blockIdx.x; r[3] = blockIdx.y | (blockIdx.z << 16);
+  r[4] = threadIdx.x | (blockDim.x << 16); r[5] = tag; r[6] = lo; r[7] = hi;
   __threadfence_system();
 }
 // try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes or the

@@ -201,14 +201,6 @@ struct EngineBase {
                r.thread >> 16, (r.thread & 0xFFFFu) >> 5, r.bar & 0x7FFFFFFFu, r.bar >> 31, r.state_hi, r.state_lo, describe_wait(r).c_str());
       out += b;
     }
-    snprintf(b, sizeof b, "  shared-memory words from 0x%x (%u x 8 B, dynamic smem %u B) of cta(%u,...) of record 0:\n   ", lg->dump_base,
-             lg->dump_words, lg->smem_bytes, lg->rec[0].cta_x);
-    out += b;
-    for (uint32_t i = 0; i < lg->dump_words && i < (uint32_t)kWaitDumpWords; ++i) {
-      snprintf(b, sizeof b, " %016llx%s", (unsigned long long)lg->dump[i], (i % 8 == 7) ? "\n   " : "");
-      out += b;
-    }
-    out += "\n";
     return out;
   }
   int fail(int code, const char* fmt, ...) {
@@ -1327,12 +1319,8 @@ struct Engine : EngineBase {
         SkParams& q = o.sp;
         q.epi12 = (!no_epi12 && q.xf == 0 && q.taps == 1 && q.rowstats_out == nullptr) ? 1 : 0;   // the small-K, epilogue-bound ops
         const bool uses_r = q.resid_mode != 0 || q.has_out_r != 0;
-        if (o.BN == 256) sk_pick_rings<256>(q.taps, q.xf, uses_r, q.epi12, q.na, q.nb, q.nr);
-        else sk_pick_rings<128>(q.taps, q.xf, uses_r, q.epi12, q.na, q.nb, q.nr);
-        if (getenv("SFB_RINGS_STATIC")) {      // A/B aid: the fixed depths of the first sk kernel
-          q.na = o.BN == 256 ? 2 : 3; q.nb = o.BN == 256 ? 3 : 5; q.nr = 4;
-          if (q.epi12 && SkCfg<256>::smem_bytes(q.na, q.nb, q.nr, 1) > SkCfg<256>::kMaxSmem && o.BN == 256) q.nr = 3;
-        }
+        if (o.BN == 256) sk_pick_rings<256>(q.taps, q.xf, uses_r, q.resid_mode != 0, q.epi12, q.na, q.nb, q.nr);
+        else sk_pick_rings<128>(q.taps, q.xf, uses_r, q.resid_mode != 0, q.epi12, q.na, q.nb, q.nr);
       }
     }
     if (!fold_items.empty()) {

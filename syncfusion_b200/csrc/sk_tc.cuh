@@ -85,15 +85,18 @@ template <int BN> struct SkCfg {
 // Ring depths per op class under the 227 KB budget (host side).  The mainloop of the k = 3 convs wants A stages (load ->
 // in-place transform -> MMA each hold one), the HBM-bound 1 x 1 ops want residual chunks in flight.
 template <int BN>
-inline void sk_pick_rings(int taps, int xf, bool uses_r, int epi12, int& na, int& nb, int& nr) {
+inline void sk_pick_rings(int taps, int xf, bool uses_r, bool has_resid, int epi12, int& na, int& nb, int& nr) {
   using C = SkCfg<BN>;
+  const int npar = epi12 ? 3 : 2;           // epilogue chunk groups
   if (taps == 3) { na = uses_r ? 3 : 4; nr = uses_r ? 3 : 0; }
   else if (epi12) { na = uses_r ? 2 : 3; nr = uses_r ? 5 : 0; }
   else { na = 2; nr = uses_r ? 4 : 0; }
+  if (uses_r && !has_resid) nr = npar;      // plain output staging: exactly one private slot per chunk group
+  const int nr_min = uses_r ? (has_resid ? 2 : npar) : 0;
   auto fits = [&](int a, int b2, int r) { return C::smem_bytes(a, b2, r, epi12) <= C::kMaxSmem; };
   nb = taps == 3 ? C::MAX_NB : na + 1;      // one weight tile per tap: a 1 x 1 op never runs further ahead on B than on A
   while (nb > 2 && !fits(na, nb, nr)) --nb;
-  while (!fits(na, nb, nr) && nr > 2) --nr;
+  while (!fits(na, nb, nr) && nr > nr_min) --nr;
   while (!fits(na, nb, nr) && na > 2) --na;
 }
 
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&op_full[s], 128); }
     for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], epi12 ? 384 : 256); }
-    for (int s = 0; s < NR; ++s) { mbar_init(&rc_full[s], 1); mbar_init(&rc_empty[s], 4); }
+    for (int s = 0; s < NR; ++s) { mbar_init(&rc_full[s], 1); mbar_init(&rc_empty[s], epi12 ? 12 : 8); }   // every epilogue warp, once per fill
     fence_barrier_init();
   }
   if (warp == 3) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
@@ -464,9 +467,26 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
     };
     uint32_t i = 0;
     int prev_slot = -1;                 // R slot of this warp's previous chunk (handed back once its store was read)
-    int rs = 0;                         // R slot / phase of the chunk this warp works on (advanced by the chunk stride)
+    int rs = 0;                         // R slot / phase of chunk q_cur
     uint32_t phr = 0;
-    uint32_t q_cur = 0;                 // global chunk index rs / phr correspond to
+    uint32_t q_cur = 0;                 // next global chunk index this warp has not yet passed (its own or another group's)
+    // Residual ring protocol.  The chunk groups take ALTERNATE chunks of one shared ring, so a warp works on only every
+    // npar-th fill of a slot - but an mbarrier wait knows a phase by its PARITY only: a warp that skipped a fill cannot tell
+    // "my fill landed" from "the fill two phases earlier landed" and would run ahead of the producer on stale data, after
+    // which the arrival accounting of rc_empty is off and the ring deadlocks (the r1 hang: seen as all epilogue warps
+    // parked on rc_full while the producer waits for a release that was counted one phase early).  Hence every warp
+    // PASSES EVERY chunk in order: for a chunk of another group lane 0 waits for its fill and hands the slot straight
+    // back (it never touches the data), so each warp observes every phase of every slot and rc_empty counts every
+    // epilogue warp once per fill (init count = number of epilogue warps).
+    auto pass_foreign_chunks = [&](uint32_t upto) {
+      for (; q_cur < upto; ++q_cur) {
+        if (resid_mode != 0 && lane == 0) {
+          mbar_wait(&rc_full[rs], phr);
+          mbar_arrive(&rc_empty[rs]);
+        }
+        if (++rs == NR) { rs = 0; phr ^= 1; }
+      }
+    };
     for (int t = t_begin; t < t_end; ++t, ++i) {
       const int n_idx = t % p.n_tiles;
       const int n0 = n_idx * BN;
@@ -536,8 +556,6 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
 #pragma unroll 1
       for (int c = par; c < NCH; c += npar) {
         const uint32_t qg = i * NCH + c;           // chunk counter shared with the residual producer
-        for (; q_cur < qg; ++q_cur) if (++rs == NR) { rs = 0; phr ^= 1; }
-        uint8_t* rt = sR + rs * C::R_BYTES;         // [128 rows][128 B], 128B swizzle
         uint32_t v[32];
         tmem_ld32(tacc + c * 32, v);
         if (et == 0) SK_STAMP(4, 4 * (qg >> 1));
@@ -548,7 +566,14 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           if (resid_mode != 0 && prev_slot >= 0) mbar_arrive(&rc_empty[prev_slot]);
           prev_slot = -1;
         }
-        __syncwarp();
+        pass_foreign_chunks(qg);                   // lane 0 observes + releases the other groups' chunks before qg
+        __syncwarp();                              // ... so every lane's parity wait below is phase-exact
+        // Residual ops: the R slot of this chunk (filled by the TMA producer, handed back through rc_empty).  Ops WITHOUT a
+        // residual use the R ring as plain output staging: each chunk group owns slot `par` outright - a slot shared between
+        // warps of different groups would be rewritten by one warp while the other warp's TMA store still reads it (only
+        // the issuing thread's bulk_wait_read orders a store against later writes).  sk_pick_rings keeps nr >= npar.
+        uint8_t* rt = sR + (resid_mode != 0 ? rs : par) * C::R_BYTES;         // [128 rows][128 B], 128B swizzle
+        const int my_slot = rs;
         if (resid_mode != 0) mbar_wait(&rc_full[rs], phr);
         tmem_ld_wait();
         if (c + npar >= NCH) {        // this thread's last TMEM read of the tile: hand the accumulator back
@@ -637,10 +662,12 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
           if (et == 0) SK_STAMP(4, 4 * (qg >> 1) + 3);
           if (epi12 && resid_mode != 0) {      // three warps per sub-partition hide this wait; the slot returns a chunk earlier
             bulk_wait_read<0>();
-            mbar_arrive(&rc_empty[rs]);
+            mbar_arrive(&rc_empty[my_slot]);
           }
         }
-        prev_slot = epi12 ? -1 : rs;
+        prev_slot = epi12 ? -1 : my_slot;
+        ++q_cur;                               // this warp's own chunk is passed
+        if (++rs == NR) { rs = 0; phr ^= 1; }
       }
       if (p.rowstats_out != nullptr && row_valid) {      // two partial sums per (row, n tile): one per chunk parity
         float* dst = p.rowstats_out + (((size_t)b * p.L + l0 + row) * (2 * p.n_tiles) + 2 * n_idx + par) * 2;
@@ -648,6 +675,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
         dst[1] = rq0 + rq1;
       }
     }
+    pass_foreign_chunks((uint32_t)(t_end - t_begin) * NCH);     // trailing chunks of the other groups (uniform accounting)
     flush_stats(cur_b, cur_goff);
     if (lane == 0) {                    // every thread that issued stores waits for its bulk groups before exit
       if (et == 0) SK_STAMP(7, 1);

@@ -259,42 +259,114 @@ class VSampler:
     __call__ = forward
 
 
-class DiffusionModel:
+class DiffusionModel(torch.nn.Module):
     """``audio_diffusion_pytorch.DiffusionModel`` stand-in for the sampling path (exp/model/diffusion.yaml:11-33).
 
     ``model.sample(x_noisy=noise, num_steps=N, channels=y_latent['xs'][2:-1], embedding=z_latent,
-    embedding_scale=s)`` works exactly as at main/generation.py:77-83.  Training (``forward`` = VDiffusion loss,
-    main/module_diffusion.py:77) is outside the hot path and raises.
+    embedding_scale=s)`` works exactly as at main/generation.py:77-83.  It is an ``nn.Module`` WITHOUT parameters (the
+    weights live re-packed inside ``libsyncfusion_b200.so``), so it can sit where the reference keeps it - as
+    ``Model.model`` of the Lightning module (main/module_diffusion.py:39) - and the reference's own calls reach it:
+
+    * ``Model.load_state_dict(checkpoint['state_dict'])`` (main/generation.py:42-43) recurses into
+      ``_load_from_state_dict`` below, which consumes every ``model.*`` key (nested oracle / checkpoint names or flat
+      C-ABI names) and reports missing / unexpected ones like any module;
+    * ``Model.to(device)`` (main/generation.py:44) moves the zero-size anchor buffer; the C engine is created on that
+      device at the first use (or eagerly when a CUDA ``device`` is given to the constructor);
+    * ``list(Model.model.parameters())`` (main/module_diffusion.py:55) is empty.
+
+    Training (``forward`` = VDiffusion loss, main/module_diffusion.py:77) is outside the hot path and raises.
     """
 
-    def __init__(self, cfg: UNetConfig = UNetConfig(), device: "torch.device | str | int" = "cuda"):
+    def __init__(self, cfg: UNetConfig = UNetConfig(), device: "torch.device | str | int | None" = None):
+        super().__init__()
         self.cfg = cfg
-        self.net = UNetV0(cfg, device)
-        self.sampler = VSampler(self.net)
+        self.register_buffer("_anchor", torch.empty(0), persistent=False)     # follows .to(device) / .cuda()
+        self._staged: Dict[str, Tensor] = {}        # flat name -> fp32 CPU tensor, until the engine is finalized
+        self._net: Optional[UNetV0] = None
+        self._sampler: Optional[VSampler] = None
+        if device is not None:
+            dev = torch.device(device)
+            if dev.type != "cuda":
+                raise _lib.SfbError(f"device must be CUDA, got {dev}")
+            if not torch.cuda.is_available():
+                raise _lib.SfbError("syncfusion_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+            self._anchor = self._anchor.to(torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device()))
+            self._net = UNetV0(cfg, self._anchor.device)      # eager: constructing with a device needs the B200 + library
+            self._sampler = VSampler(self._net)
 
+    # ------------------------------------------------------------------ engine life cycle
     @property
     def device(self) -> torch.device:
-        return self.net.device
+        return self._anchor.device
 
-    def load_state_dict(self, state_dict: Mapping[str, Tensor], strict: bool = True):
-        self.net.load_state_dict(state_dict, strict)
-        return self
+    def _engine(self) -> UNetV0:
+        """The C engine on this module's device: created at first use, fed with the staged parameters and finalized."""
+        dev = self._anchor.device
+        if dev.type != "cuda":
+            raise _lib.SfbError("syncfusion_b200.DiffusionModel is on the CPU: move it with .to('cuda') first "
+                                "(the sampling path is CUDA-only, there is no CPU fallback)")
+        if self._net is not None and self._net.device != dev:
+            if not self._staged:
+                raise _lib.SfbError(f"the engine was finalized on {self._net.device}; re-load the state dict to move it to {dev}")
+            self._net = None
+        if self._net is None:
+            self._net = UNetV0(self.cfg, dev)
+            self._sampler = VSampler(self._net)
+        if not self._net._finalized:
+            if not self._staged:
+                raise AssertionError("load_state_dict() first")
+            self._net.load_state_dict(self._staged)
+            self._staged = {}                          # the library holds the re-packed copies now
+        return self._net
 
-    def eval(self):
-        return self
+    @property
+    def net(self) -> UNetV0:
+        return self._engine()
 
-    def to(self, device):
-        assert torch.device(device).type == "cuda"
-        return self
+    @property
+    def sampler(self) -> VSampler:
+        self._engine()
+        return self._sampler
 
+    # ------------------------------------------------------------------ state dict (main/generation.py:40-43)
+    def _stage(self, state_dict: Mapping[str, Tensor], prefix: str, strict: bool, missing: list, unexpected: list, errors: list):
+        from .synth import param_shapes
+        want = param_shapes(self.cfg)
+        got: Dict[str, Tensor] = {}
+        for k, v in state_dict.items():
+            if not k.startswith(prefix) or not isinstance(v, Tensor):
+                continue
+            name = flat_param_name(k[len(prefix):])
+            if name not in want:
+                unexpected.append(k)
+                continue
+            if tuple(v.shape) != want[name]:
+                errors.append(f"size mismatch for {k}: checkpoint {tuple(v.shape)} vs model {want[name]}")
+                continue
+            got[name] = v.detach().to(torch.float32).cpu().contiguous()
+        for name in want:
+            if name not in got:
+                missing.append(prefix + name)
+        if not errors and (not missing or not strict):
+            if self._net is not None and self._net._finalized:
+                self._net = None                       # re-load: a fresh engine is built from the new weights
+            self._staged = got
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # called by nn.Module.load_state_dict of THIS module or of any parent (the reference's Lightning Model)
+        self._stage(state_dict, prefix, strict, missing_keys, unexpected_keys, error_msgs)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        # the weights are owned by the C library in re-packed form; nothing to export (and nothing for a parent to save)
+        return destination if destination is not None else {}
+
+    # ------------------------------------------------------------------ the reference surface
     @torch.no_grad()
     def sample(self, *args, **kwargs) -> Tensor:
         return self.sampler(*args, **kwargs)
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError("the VDiffusion training objective is out of scope of the B200 sampling path")
-
-    __call__ = forward
 
 
 def hydra_config(net_t=None, diffusion_t=None, sampler_t=None, use_embedding_cfg: bool = True, precision: str = "bf16",
@@ -311,7 +383,7 @@ def hydra_config(net_t=None, diffusion_t=None, sampler_t=None, use_embedding_cfg
     return UNetConfig(use_embedding_cfg=bool(use_embedding_cfg), precision=precision, upsample_mode=upsample_mode, **kw)
 
 
-def hydra_target(device: "torch.device | str | int" = "cuda", **kw) -> DiffusionModel:
+def hydra_target(device: "torch.device | str | int | None" = None, **kw) -> DiffusionModel:
     """Drop-in ``_target_`` for ``model.model`` of exp/model/diffusion.yaml."""
     return DiffusionModel(hydra_config(**kw), device)
 

@@ -31,6 +31,51 @@ def _linear(g, out_f, in_f, bias=True):
     return _uniform(g, (out_f, in_f), b), (_uniform(g, (out_f,), b) if bias else None)
 
 
+def param_shapes(cfg: UNetConfig) -> Dict[str, Tuple[int, ...]]:
+    """Flat C-ABI parameter name -> shape for this configuration: exactly the set ``sfb_finalize`` requires (used by
+    ``DiffusionModel.load_state_dict(strict=True)`` to report missing / unexpected keys without allocating weights)."""
+    sh: Dict[str, Tuple[int, ...]] = {}
+    mf, ef = cfg.modulation_features, cfg.embedding_features
+    mid = cfg.attention_heads * cfg.attention_features
+    sh["time.weights"] = (128,)
+    sh["time.linear.weight"], sh["time.linear.bias"] = (mf, 257), (mf,)
+    sh["time.mlp.weight"], sh["time.mlp.bias"] = (mf, mf), (mf,)
+    sh["fixed_embedding.weight"] = (cfg.embedding_max_length, ef)
+    for d in range(cfg.depth):
+        c, f, ctx = cfg.channels[d], cfg.factors[d], cfg.context_channels[d]
+        cin = cfg.in_channels if d == 0 else cfg.channels[d - 1]
+        p = f"d{d}."
+        sh[p + "down.weight"], sh[p + "down.bias"] = (c, cin, f), (c,)
+        if cfg.upsample_mode == "transpose":
+            sh[p + "up.weight"], sh[p + "up.bias"] = (c, cin, f), (cin,)
+        else:
+            sh[p + "up.conv.weight"], sh[p + "up.conv.bias"] = (cin, c, 3), (cin,)
+        sh[p + "skip.weight"], sh[p + "skip.bias"] = (cin, mf), (cin,)
+        for stack in ("items_down", "items_up"):
+            for i in range(cfg.items[d]):
+                q = f"{p}{stack}.{i}."
+                for n in ("gn1", "gn2"):
+                    sh[q + f"resnet.{n}.weight"] = sh[q + f"resnet.{n}.bias"] = (c,)
+                for n in ("conv1", "conv2"):
+                    sh[q + f"resnet.{n}.weight"], sh[q + f"resnet.{n}.bias"] = (c, c, 3), (c,)
+                sh[q + "mod.linear.weight"], sh[q + "mod.linear.bias"] = (2 * c, mf), (2 * c,)
+                if ctx > 0:
+                    sh[q + "inject.conv.weight"], sh[q + "inject.conv.bias"] = (c, c + ctx, 1), (c,)
+                kinds = []
+                if cfg.attentions[d]:
+                    kinds.append(("attn", c))
+                if cfg.cross_attentions[d]:
+                    kinds.append(("xattn", ef))
+                for name, cf in kinds:
+                    a = q + f"{name}.attn."
+                    sh[a + "norm.weight"] = sh[a + "norm.bias"] = (c,)
+                    sh[a + "norm_ctx.weight"] = sh[a + "norm_ctx.bias"] = (cf,)
+                    sh[a + "to_q.weight"] = (mid, c)
+                    sh[a + "to_kv.weight"] = (2 * mid, cf)
+                    sh[a + "to_out.weight"] = (c, mid)
+    return sh
+
+
 def random_state_dict(cfg: UNetConfig, seed: int = 0) -> Dict[str, Tensor]:
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, Tensor] = {}
