@@ -95,6 +95,46 @@ int sfb_sample(sfb_handle* h, const float* x_noisy, int num_steps, const float* 
 /* Number of kernels the last sfb_sample / sfb_unet_forward call enqueued (bench.py's gpu_launches). */
 int64_t sfb_last_launch_count(const sfb_handle* h);
 
+/* ---- onset encoder: the producer of `channels` -------------------------------------------------
+ * Replaces audio_encoders_pytorch.Encoder1d as configured at exp/model/diffusion.yaml:35-43 and called at
+ * main/generation.py:71 / main/module_diffusion.py:196 (`_, y_latent = model.onsets_encoder(y, with_info=True)`).
+ * Field-for-field mirror of the yaml block: */
+typedef struct sfb_encoder_config {
+  int32_t in_channels;                        /* :37  1 */
+  int32_t channels;                           /* :38  2 */
+  int32_t n_levels;                           /* len(factors) = 8 */
+  int32_t multipliers[SFB_MAX_DEPTH + 1];     /* :39  [1,1,4,8,16,32,64,128,128] */
+  int32_t factors[SFB_MAX_DEPTH];             /* :40  [1,4,4,4,2,2,2,2] */
+  int32_t num_blocks[SFB_MAX_DEPTH];          /* :41  [2]*8 */
+  int32_t resnet_groups;                      /* :42  2 */
+  int32_t patch_size;                         /* :43  1 */
+} sfb_encoder_config;
+typedef struct sfb_encoder sfb_encoder;
+int sfb_encoder_create(const sfb_encoder_config* cfg, int device, sfb_encoder** out);
+void sfb_encoder_destroy(sfb_encoder* h);
+const char* sfb_encoder_last_error(const sfb_encoder* h);
+/* Parameters under the upstream module names ("to_in.block1.groupnorm.weight", "downsamples.3.downsample.weight",
+ * "downsamples.3.blocks.1.block2.project.bias", ...); f32, host or device pointer; copied. */
+int sfb_encoder_set_param(sfb_encoder* h, const char* name, const void* data, const int64_t* shape, int ndim);
+int sfb_encoder_finalize(sfb_encoder* h);
+/* Output length of pyramid level `level` (0 .. n_levels-1; -1: the to_in output = L) for an input of L samples. */
+int64_t sfb_encoder_level_length(sfb_encoder* h, int64_t L, int level);
+int sfb_encoder_workspace_bytes(sfb_encoder* h, int64_t B, int64_t L, size_t* out);
+/* y [B, in_channels, L] f32 -> xs_out[0] = to_in(y) [B, channels*m0, L], xs_out[1 + i] = level i [B, channels*m_{i+1}, L_i]
+ * (NCL f32 device buffers, n_out = n_levels + 1): info['xs'][1:-1] of the reference; the last one is also z. */
+int sfb_encoder_forward(sfb_encoder* h, const float* y, int64_t B, int64_t L, float* const* xs_out, int n_out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Generation post-processing for a whole batch (main/generation.py:85-98), one pass on the GPU:
+ *   cut_prefix (onsets != NULL): gen[i, :, :first_onset_i] = 0 with first_onset_i = first non-zero sample of onsets[i]
+ *   (:86-88; first_onset [B] int32 device buffer receives it, L for a track with no onset - the reference raises there);
+ *   crop to cut_length (:90,:96); new_freq != 0: torchaudio.functional.resample(orig_freq -> new_freq) (:90-92).
+ * gen / onsets [B, 1, L] f32, out [B, 1, out_len] f32 with out_len = sfb_postprocess_out_len(...); device pointers.
+ * No handle: the resampling tap table is cached per (device, rate pair). */
+int64_t sfb_postprocess_out_len(int64_t cut_length, int orig_freq, int new_freq);
+int sfb_postprocess(int device, const float* gen, const float* onsets, int64_t B, int64_t L, int64_t cut_length, int orig_freq,
+                    int new_freq, float* out, int64_t out_len, int* first_onset, void* stream);
+
 /* ---- test / profiling hooks (stable, but not part of the reference surface) -------------------------------- */
 /* Stop every U-Net evaluation after `n_ops` plan operations (<0: run everything). */
 int sfb_dbg_set_op_limit(sfb_handle* h, int n_ops);
@@ -102,6 +142,10 @@ int sfb_dbg_set_op_limit(sfb_handle* h, int n_ops);
  * "kind depth stack item out_offset out_bytes rows cols dtype". */
 int sfb_dbg_plan_size(sfb_handle* h, int64_t B, int64_t L, int cfg_on, void* workspace, size_t workspace_bytes);
 int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len);
+/* Launch the persistent kernels (streaming-K / resident-weight / generic GEMM) with at most `max_ctas` CTAs (0: one per
+ * SM).  Process-wide.  Fewer CTAs = more tiles per CTA: the parity tests use it to drive the shared-memory rings, the
+ * TMEM double buffer and the residual-slot recycling through many wrap-arounds on shapes the oracle still handles. */
+int sfb_dbg_set_grid_limit(sfb_handle* h, int max_ctas);
 /* Post-mortem of a device barrier-wait timeout.  Every mbarrier wait of the tcgen05 / TMA pipelines is bounded
  * (about 8 s when nothing arrives); a waiter that hits the bound records {kernel source line, plan op, CTA, thread,
  * barrier, parity, raw barrier word} in a host-mapped log and traps, so the launch ends in a CUDA error instead of a

@@ -12,8 +12,9 @@ SFB_MAX_DEPTH = 16
 
 EXPORTS = [
     "sfb_create", "sfb_destroy", "sfb_last_error", "sfb_set_param", "sfb_finalize", "sfb_workspace_bytes",
-    "sfb_unet_forward", "sfb_sample", "sfb_last_launch_count", "sfb_dbg_set_op_limit", "sfb_dbg_plan_size",
-    "sfb_dbg_op_info", "sfb_dbg_wait_log", "sfb_dbg_fault_inject", "sfb_dbg_sk_timeline", "sfb_dbg_profile", "sfb_dbg_profile_report", "sfb_dbg_gemm", "sfb_dbg_attention",
+    "sfb_unet_forward", "sfb_sample", "sfb_last_launch_count", "sfb_postprocess", "sfb_postprocess_out_len", "sfb_encoder_create", "sfb_encoder_destroy", "sfb_encoder_last_error",
+    "sfb_encoder_set_param", "sfb_encoder_finalize", "sfb_encoder_level_length", "sfb_encoder_workspace_bytes", "sfb_encoder_forward", "sfb_dbg_set_op_limit", "sfb_dbg_plan_size",
+    "sfb_dbg_op_info", "sfb_dbg_wait_log", "sfb_dbg_fault_inject", "sfb_dbg_set_grid_limit", "sfb_dbg_sk_timeline", "sfb_dbg_profile", "sfb_dbg_profile_report", "sfb_dbg_gemm", "sfb_dbg_attention",
 ]
 
 
@@ -26,6 +27,14 @@ class SfbUnetConfig(C.Structure):
         ("attention_heads", C.c_int32), ("attention_features", C.c_int32), ("embedding_features", C.c_int32),
         ("embedding_max_length", C.c_int32), ("resnet_groups", C.c_int32), ("modulation_features", C.c_int32),
         ("upsample_mode", C.c_int32), ("precision", C.c_int32),
+    ]
+
+
+class SfbEncoderConfig(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int32), ("channels", C.c_int32), ("n_levels", C.c_int32),
+        ("multipliers", C.c_int32 * (SFB_MAX_DEPTH + 1)), ("factors", C.c_int32 * SFB_MAX_DEPTH),
+        ("num_blocks", C.c_int32 * SFB_MAX_DEPTH), ("resnet_groups", C.c_int32), ("patch_size", C.c_int32),
     ]
 
 
@@ -58,11 +67,29 @@ def load() -> C.CDLL:
     lib.sfb_sample.argtypes = [vp, vp, i32, C.POINTER(vp), i32, vp, i64, f32, vp, vp, vp, vp, i64, i64, vp,
                                C.c_size_t, vp]
     lib.sfb_last_launch_count.argtypes = [vp]
+    if hasattr(lib, "sfb_encoder_create"):
+        lib.sfb_encoder_create.argtypes = [C.POINTER(SfbEncoderConfig), i32, C.POINTER(vp)]
+        lib.sfb_encoder_destroy.argtypes = [vp]
+        lib.sfb_encoder_destroy.restype = None
+        lib.sfb_encoder_last_error.argtypes = [vp]
+        lib.sfb_encoder_last_error.restype = C.c_char_p
+        lib.sfb_encoder_set_param.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
+        lib.sfb_encoder_finalize.argtypes = [vp]
+        lib.sfb_encoder_level_length.argtypes = [vp, i64, i32]
+        lib.sfb_encoder_level_length.restype = i64
+        lib.sfb_encoder_workspace_bytes.argtypes = [vp, i64, i64, C.POINTER(C.c_size_t)]
+        lib.sfb_encoder_forward.argtypes = [vp, vp, i64, i64, C.POINTER(vp), i32, vp, C.c_size_t, vp]
+    if hasattr(lib, "sfb_postprocess"):
+        lib.sfb_postprocess_out_len.argtypes = [i64, i32, i32]
+        lib.sfb_postprocess_out_len.restype = i64
+        lib.sfb_postprocess.argtypes = [i32, vp, vp, i64, i64, i64, i32, i32, vp, i64, vp, vp]
     lib.sfb_last_launch_count.restype = i64
     lib.sfb_dbg_set_op_limit.argtypes = [vp, i32]
     lib.sfb_dbg_plan_size.argtypes = [vp, i64, i64, i32, vp, C.c_size_t]
     lib.sfb_dbg_op_info.argtypes = [vp, i32, C.c_char_p, i32]
     lib.sfb_dbg_sk_timeline.argtypes = [vp, i32, vp, i32]
+    if hasattr(lib, "sfb_dbg_set_grid_limit"):
+        lib.sfb_dbg_set_grid_limit.argtypes = [vp, i32]
     if not (os.environ.get("SFB_LIB") and not hasattr(lib, "sfb_dbg_wait_log")):   # an older A/B build may lack these two
         lib.sfb_dbg_wait_log.argtypes = [vp, C.c_char_p, i32]
         lib.sfb_dbg_fault_inject.argtypes = [vp, vp]
@@ -71,7 +98,7 @@ def load() -> C.CDLL:
     lib.sfb_dbg_gemm.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.sfb_dbg_attention.argtypes = [i32, vp, vp, i32, i32, vp]
     for name in EXPORTS:          # every symbol the header declares must resolve
-        if os.environ.get("SFB_LIB") and name in ("sfb_dbg_wait_log", "sfb_dbg_fault_inject") and not hasattr(lib, name):
+        if os.environ.get("SFB_LIB") and (name in ("sfb_dbg_wait_log", "sfb_dbg_fault_inject", "sfb_dbg_set_grid_limit", "sfb_postprocess", "sfb_postprocess_out_len") or name.startswith("sfb_encoder_")) and not hasattr(lib, name):
             continue
         getattr(lib, name)
     _lib = lib

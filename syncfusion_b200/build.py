@@ -10,7 +10,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libsyncfusion_b200.so"
 SOURCES = ["sfb.cu"]
-HEADERS = ["ptx.cuh", "gemm_tc.cuh", "attn_tc.cuh", "elementwise.cuh", "d0.cuh", "prepare.cuh", "rk_tc.cuh", "sk_tc.cuh"]
+HEADERS = ["ptx.cuh", "gemm_tc.cuh", "attn_tc.cuh", "elementwise.cuh", "encoder.cuh", "d0.cuh", "prepare.cuh", "postprocess.cuh", "rk_tc.cuh", "sk_tc.cuh"]
 
 
 def _nvcc() -> str:
@@ -28,19 +28,26 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, wait_log: "int | None" = None, out: "Path | None" = None) -> Path:
+    """wait_log: record level of the bounded barrier waits (csrc/ptx.cuh; default 1, 2 = one record per stuck waiter);
+    out: library path (default: the in-tree libsyncfusion_b200.so the package loads)."""
+    target = Path(out) if out else LIB
+    if not force and out is None and wait_log is None and not needs_build():
         return LIB
+    level = wait_log if wait_log is not None else (int(os.environ["SFB_WAIT_LOG"]) if os.environ.get("SFB_WAIT_LOG") else None)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-           "--use_fast_math" if False else "-DSFB_NO_FAST_MATH", *(["-DSFB_RK_PIPE"] if os.environ.get("SFB_RK_PIPE") else []), "-Xcompiler", "-fPIC", "-shared",
-           "-Xptxas", "-v" if verbose else "-O3", "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+           "-DSFB_NO_FAST_MATH", *(["-DSFB_RK_PIPE"] if os.environ.get("SFB_RK_PIPE") else []),
+           *([f"-DSFB_WAIT_LOG={level}"] if level is not None else []), "-Xcompiler", "-fPIC", "-shared",
+           "-Xptxas", "-v" if verbose else "-O3", "-o", str(target)] + [str(CSRC / s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    lvl = int(sys.argv[sys.argv.index("--wait-log") + 1]) if "--wait-log" in sys.argv else None
+    dst = Path(sys.argv[sys.argv.index("-o") + 1]) if "-o" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, wait_log=lvl, out=dst))

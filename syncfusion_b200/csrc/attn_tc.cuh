@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   pdl_wait();            // everything above is independent of the previous kernel's output
+  mark_progress(p.tag);
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + BKV;

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kGemmThreads, GemmCfg<BN>::kCtasPerSm) gemm_tc
   tc_fence_before();
   __syncthreads();
   pdl_wait();            // everything above is independent of the previous kernel's output
+  mark_progress(p.tag);
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

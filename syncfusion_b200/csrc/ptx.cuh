@@ -56,36 +56,76 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait with a post-mortem record.  A waiter polls the hinted try_wait below; when the poll count passes
-// c_wait_bound (2^21: >= 30 ms of continuously woken polling - 30x any healthy wait of these kernels - or ~8 s of
-// parked polling, a parked poll lasts ~4 us on B200, tools/trywait_bench.cu) lane 0 of the warp writes ONE record
-// {call site, barrier address, parity, CTA, thread, op tag, raw barrier word} into a host-mapped log, keeps polling
-// for another 2^17 polls so that the other stuck roles of the grid get their records in, and traps.  The host
-// (sfb.cu: wait_log_text) decodes the log into sfb_last_error(): a pipeline bug ends in seconds with the kernel, the
-// role and the barrier named, instead of a hung GPU.  The hot loop stays {try_wait, add, compare, branch}: everything
-// else is in the cold block (measured in r1: any extra instruction in the loop costs 2-5 % of the whole step).
+// Bounded wait with a post-mortem record.  A waiter polls the hinted try_wait below; when its poll count passes
+// 2^SFB_WAIT_BOUND_LOG2 (default 2^21: >= 30 ms of continuously woken polling - 30x any healthy wait of these kernels
+// - or ~8 s of parked polling; a parked poll lasts ~4 us on B200, tools/trywait_bench.cu) it leaves a record in a
+// host-mapped log and traps, so a pipeline bug ends in seconds with a CUDA error that names the kernel, the plan op and
+// the wait site instead of hanging the GPU (host side: sfb.cu wait_log_text -> sfb_last_error()).
+// Two record levels (SFB_WAIT_LOG, build time), because the cold code at ~25 wait sites per kernel is not free:
+//   1 (default)  the waiter stores {call site, CTA, thread} to fixed words (last writer wins) and traps: ~8
+//                instructions per site, nothing live across them.  The plan op comes from the progress marker every
+//                kernel writes after griddepcontrol.wait (mark_progress: the last op that started is the stuck one).
+//   2            full per-waiter records {site, barrier address + parity, CTA, thread, op, raw barrier word} through ONE
+//                out-of-line noreturn function, then ~20 ms of lingering so the other stuck roles record too.
+//                (+10 % SASS per kernel, measured -4 % end to end; inlining the record cost 11 % on sk_kernel, a
+//                returning call 11 % on the attention kernel.)  python -m syncfusion_b200.build --wait-log 2
+//   0            trap only.
+#ifndef SFB_WAIT_BOUND_LOG2
+#define SFB_WAIT_BOUND_LOG2 21
+#endif
+#ifndef SFB_WAIT_LOG
+#define SFB_WAIT_LOG 1
+#endif
 struct WaitRecord { uint32_t site, bar, cta_x, cta_yz, thread, tag, state_lo, state_hi; };
 constexpr int kWaitRecMax = 120;
 struct WaitLog {
-  uint32_t count, pad[7];
+  uint32_t count;                 // level 2: number of records
+  uint32_t cur_tag;               // progress marker: plan op of the most recently started kernel (0xFFFFFFFF: none)
+  uint32_t light_site, light_cta, light_thread, light_flag;      // level 1: last stuck waiter (flag = 1 once written)
+  uint32_t pad[2];
   WaitRecord rec[kWaitRecMax];
 };
 __device__ WaitLog* g_wait_log = nullptr;            // device pointer of the host-mapped log (sfb_create)
-__constant__ uint32_t c_wait_bound = 1u << 21;       // SFB_WAIT_BOUND_LOG2 overrides (compute-sanitizer runs)
 
-// Inlined on purpose: as a __noinline__ call the ABI's register constraints made the 168-register attention kernel
-// spill (+11 % on that kernel); inlined, the cold block needs a handful of scratch registers at the wait site only.
-__device__ __forceinline__ void wait_timeout_report(uint32_t bar, uint32_t parity, uint32_t site, uint32_t tag) {
+// Every kernel of the chain calls this right after griddepcontrol.wait (the previous grid has completed): one
+// fire-and-forget store per launch.
+__device__ __forceinline__ void mark_progress(int tag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    WaitLog* lg = g_wait_log;
+    if (lg != nullptr) *reinterpret_cast<volatile uint32_t*>(&lg->cur_tag) = (uint32_t)tag;
+  }
+}
+
+__device__ __noinline__ __attribute__((noreturn)) void wait_timeout_trap(uint32_t bar, uint32_t parity, uint32_t site, uint32_t tag) {
   WaitLog* lg = g_wait_log;
-  if (lg == nullptr) return;
-  const uint32_t slot = atomicAdd(&lg->count, 1u);
-  if (slot >= (uint32_t)kWaitRecMax) return;
-  uint32_t lo, hi;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(bar));
-  volatile uint32_t* r = reinterpret_cast<volatile uint32_t*>(&lg->rec[slot]);
-  r[0] = site; r[1] = bar | (parity << 31); r[2] = blockIdx.x; r[3] = blockIdx.y | (blockIdx.z << 16);
-  r[4] = threadIdx.x | (blockDim.x << 16); r[5] = tag; r[6] = lo; r[7] = hi;
+  if (lg != nullptr && lane_id() == 0) {
+    const uint32_t slot = atomicAdd(&lg->count, 1u);
+    if (slot < (uint32_t)kWaitRecMax) {
+      uint32_t lo, hi;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(bar));
+      volatile uint32_t* r = reinterpret_cast<volatile uint32_t*>(&lg->rec[slot]);
+      r[0] = site; r[1] = bar | (parity << 31); r[2] = blockIdx.x; r[3] = blockIdx.y | (blockIdx.z << 16);
+      r[4] = threadIdx.x | (blockDim.x << 16); r[5] = tag; r[6] = lo; r[7] = hi;
+    }
+    __threadfence_system();
+  }
+  for (int i = 0; i < 200; ++i) __nanosleep(100000);     // ~20 ms: let the other stuck waiters record before the grid dies
   __threadfence_system();
+  __trap();
+  while (true) {}
+}
+// Level 1: out of line, noreturn, ONE immediate argument - a wait site costs {mov, call} and pins no register.  (Written
+// inline with blockIdx / threadIdx the compiler hoisted the packed words to the kernel entry and held two registers for
+// the whole 128-register sk kernel: -3 % end to end.)
+__device__ __noinline__ __attribute__((noreturn)) void wait_trap_light(uint32_t site) {
+  WaitLog* lg = g_wait_log;
+  if (lg != nullptr) {
+    volatile uint32_t* w = reinterpret_cast<volatile uint32_t*>(&lg->light_site);
+    w[0] = site; w[1] = blockIdx.x | (blockIdx.y << 16) | (blockIdx.z << 24); w[2] = threadIdx.x | (blockDim.x << 16); w[3] = 1u;
+    __threadfence_system();
+  }
+  __trap();
+  while (true) {}
 }
 // try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes or the
 // hint elapses, so a waiting warp issues almost nothing (it does not compete with the working warps of its
@@ -106,11 +146,17 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, uint32_t site, uint32_t tag) {
   uint32_t spins = 0;
   while (!mbar_try_wait_hint(bar, parity)) {
-    if (++spins >= c_wait_bound) {
-      if (spins == c_wait_bound) { if (lane_id() == 0) wait_timeout_report(smem_u32(bar), parity, site, tag); }
-      else if (spins - c_wait_bound > (1u << 17)) { __threadfence_system(); __trap(); }
+    if (__builtin_expect(++spins > (1u << SFB_WAIT_BOUND_LOG2), 0)) {      // cold: keep it out of the loop's cache lines
+#if SFB_WAIT_LOG >= 2
+      wait_timeout_trap(smem_u32(bar), parity, site, tag);
+#elif SFB_WAIT_LOG == 1
+      wait_trap_light(site);
+#else
+      __trap();
+#endif
     }
   }
+  (void)site; (void)tag;
 }
 // Call-site form: `p` is the kernel's __grid_constant__ parameter struct (its `tag` = plan op index lives in the
 // constant bank, so naming the op costs no register), SFB_FILE_ID is set by each kernel header.

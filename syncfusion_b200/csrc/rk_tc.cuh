@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
   tc_fence_before();
   __syncthreads();
   pdl_wait();            // everything above is independent of the previous kernel's output
+  mark_progress(p.tag);
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

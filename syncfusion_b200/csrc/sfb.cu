@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
+#include <numeric>
 #include <memory>
 #include <string>
 #include <vector>
@@ -18,7 +20,9 @@
 #include "attn_tc.cuh"
 #include "d0.cuh"
 #include "elementwise.cuh"
+#include "encoder.cuh"
 #include "gemm_tc.cuh"
+#include "postprocess.cuh"
 #include "prepare.cuh"
 #include "rk_tc.cuh"
 #include "sk_tc.cuh"
@@ -143,17 +147,11 @@ int wait_log_init() {
   void* h = nullptr;
   if (cudaHostAlloc(&h, sizeof(WaitLog), cudaHostAllocMapped) != cudaSuccess) return -1;
   memset(h, 0, sizeof(WaitLog));
+  reinterpret_cast<WaitLog*>(h)->cur_tag = 0xFFFFFFFFu;
   void* d = nullptr;
   if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return -1;
   WaitLog* dp = reinterpret_cast<WaitLog*>(d);
   if (cudaMemcpyToSymbol(g_wait_log, &dp, sizeof dp) != cudaSuccess) return -1;
-  if (const char* e = getenv("SFB_WAIT_BOUND_LOG2")) {
-    int lg = atoi(e);
-    if (lg >= 10 && lg <= 31) {
-      uint32_t v = 1u << lg;
-      if (cudaMemcpyToSymbol(c_wait_bound, &v, sizeof v) != cudaSuccess) return -1;
-    }
-  }
   g_wait_log_host = reinterpret_cast<WaitLog*>(h);
   return 0;
 }
@@ -188,18 +186,30 @@ struct EngineBase {
   // Text of the device wait log ("" if no wait timed out): one line per stuck waiter + the raw barrier words.
   std::string wait_log_text() {
     const WaitLog* lg = g_wait_log_host;
-    if (!lg || lg->count == 0) return "";
-    char b[512];
+    if (!lg || (lg->count == 0 && lg->light_flag == 0)) return "";
+    char b[640];
     std::string out;
-    const uint32_t n = std::min<uint32_t>(lg->count, kWaitRecMax);
-    snprintf(b, sizeof b, "barrier wait timed out: %u waiter(s) reported (first %u shown)\n", lg->count, n);
-    out += b;
-    for (uint32_t i = 0; i < n; ++i) {
-      const WaitRecord& r = lg->rec[i];
-      snprintf(b, sizeof b, "  [%u] %s:%u op#%u cta(%u,%u,%u) thread %u/%u (warp %u) bar@0x%x parity %u state 0x%08x%08x %s\n", i,
-               wait_site_file(r.site >> 16), r.site & 0xFFFFu, r.tag, r.cta_x, r.cta_yz & 0xFFFFu, r.cta_yz >> 16, r.thread & 0xFFFFu,
-               r.thread >> 16, (r.thread & 0xFFFFu) >> 5, r.bar & 0x7FFFFFFFu, r.bar >> 31, r.state_hi, r.state_lo, describe_wait(r).c_str());
+    WaitRecord cur{};
+    cur.tag = lg->cur_tag;
+    if (lg->light_flag) {      // SFB_WAIT_LOG=1 (default build): last stuck waiter + the progress marker
+      snprintf(b, sizeof b, "barrier wait timed out (device trap): %s:%u cta(%u,%u,%u) thread %u/%u (warp %u); last tensor-core op started: op#%u %s\n"
+               "  (build with SFB_WAIT_LOG=2 for one record per stuck waiter incl. barrier slot and state)\n",
+               wait_site_file(lg->light_site >> 16), lg->light_site & 0xFFFFu, lg->light_cta & 0xFFFFu, (lg->light_cta >> 16) & 0xFFu,
+               lg->light_cta >> 24, lg->light_thread & 0xFFFFu, lg->light_thread >> 16, (lg->light_thread & 0xFFFFu) >> 5, lg->cur_tag,
+               describe_wait(cur).c_str());
       out += b;
+    }
+    if (lg->count) {
+      const uint32_t n = std::min<uint32_t>(lg->count, kWaitRecMax);
+      snprintf(b, sizeof b, "barrier wait timed out: %u waiter(s) reported (first %u shown); last tensor-core op started: op#%u\n", lg->count, n, lg->cur_tag);
+      out += b;
+      for (uint32_t i = 0; i < n; ++i) {
+        const WaitRecord& r = lg->rec[i];
+        snprintf(b, sizeof b, "  [%u] %s:%u op#%u cta(%u,%u,%u) thread %u/%u (warp %u) bar@0x%x parity %u state 0x%08x%08x %s\n", i,
+                 wait_site_file(r.site >> 16), r.site & 0xFFFFu, r.tag, r.cta_x, r.cta_yz & 0xFFFFu, r.cta_yz >> 16, r.thread & 0xFFFFu,
+                 r.thread >> 16, (r.thread & 0xFFFFu) >> 5, r.bar & 0x7FFFFFFFu, r.bar >> 31, r.state_hi, r.state_lo, describe_wait(r).c_str());
+        out += b;
+      }
     }
     return out;
   }
@@ -222,6 +232,7 @@ struct EngineBase {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ GEMM launch
+int g_grid_limit = 0;     // test hook (sfb_dbg_set_grid_limit): persistent kernels use at most this many CTAs (0: all SMs)
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -229,7 +240,7 @@ int num_sms() {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
-  return n;
+  return (g_grid_limit > 0 && g_grid_limit < n) ? g_grid_limit : n;
 }
 template <typename T, int BN>
 void launch_gemm_bn(GemmParams<T> p, int B, cudaStream_t st) {
@@ -1252,6 +1263,7 @@ struct Engine : EngineBase {
     snprintf(b, sizeof b, "| %s d%d s%d i%d '%s' B=%d L=%d C=%d", kOpNames[o.kind], o.depth, o.stack, o.item, o.ck, o.B, o.L, o.C);
     std::string out = b;
     const uint32_t addr = r.bar & 0x7FFFFFFFu;
+    if (addr == 0) return out;       // light record: no barrier address
     auto name_of = [&](uint32_t bars_off, const char* const* names, const int* counts, int n) {
       const uint32_t idx = ((addr - bars_off) & 1023u) / 8;     // dynamic shared memory starts 1024-aligned
       uint32_t k = idx;
@@ -1595,12 +1607,191 @@ struct Engine : EngineBase {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ post-processing (f-2)
+// torchaudio.functional.resample's tap table, in float32 and in torchaudio's operation order (_get_sinc_resample_kernel
+// builds it in the waveform's dtype): the reference's taps carry float32 rounding that a drop-in has to reproduce.
+struct ResampleTable { int orig = 0, nw = 0, K = 0, width = 0; float* dev = nullptr; };
+static std::mutex g_post_mu;
+static std::map<std::pair<int, std::pair<int, int>>, ResampleTable> g_post_tables;   // (device, (orig_freq, new_freq))
+static const ResampleTable* resample_table(int device, int orig_freq, int new_freq) {
+  std::lock_guard<std::mutex> lk(g_post_mu);
+  auto key = std::make_pair(device, std::make_pair(orig_freq, new_freq));
+  auto it = g_post_tables.find(key);
+  if (it != g_post_tables.end()) return &it->second;
+  ResampleTable t;
+  const int g = std::gcd(orig_freq, new_freq);
+  t.orig = orig_freq / g; t.nw = new_freq / g;
+  const int lpw = 6;
+  const double base_d = std::min(t.orig, t.nw) * 0.99;
+  t.width = (int)std::ceil(lpw * t.orig / base_d);
+  t.K = 2 * t.width + t.orig;
+  const float base = (float)base_d, pi = (float)M_PI, scale = (float)(base_d / t.orig);
+  std::vector<float> h((size_t)t.nw * t.K);
+  for (int ph = 0; ph < t.nw; ++ph)
+    for (int k = 0; k < t.K; ++k) {
+      const float idx = (float)(k - t.width) / (float)t.orig;
+      volatile float tt = (float)(-ph) / (float)t.nw + idx;     // volatile: one float32 rounding per operation, no contraction
+      tt = tt * base;
+      tt = std::fmin(std::fmax((float)tt, (float)-lpw), (float)lpw);
+      volatile float w = (float)tt * pi;
+      w = w / (float)lpw; w = w / 2.f;
+      w = std::cos((float)w); w = w * w;
+      tt = tt * pi;
+      volatile float kv = ((float)tt == 0.f) ? 1.f : std::sin((float)tt) / (float)tt;
+      volatile float ws = w * scale;
+      h[(size_t)ph * t.K + k] = kv * ws;
+    }
+  if (cudaMalloc(&t.dev, h.size() * sizeof(float)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(t.dev, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return &(g_post_tables[key] = t);
+}
+
+// ------------------------------------------------------------------------------------------------ onset encoder (f-1)
+struct OnsetEncoder {
+  sfb_encoder_config cfg;
+  int device = 0;
+  std::string err;
+  std::map<std::string, HostTensor> params;
+  std::vector<void*> owned;
+  bool finalized = false;
+  struct Block { float *gn1_w, *gn1_b, *c1_w, *c1_b, *gn2_w, *gn2_b, *c2_w, *c2_b, *sc_w, *sc_b; int cin, cout, g1, g2; };
+  struct Level { float *dw, *db; int cin, cout, f; std::vector<Block> blocks; };
+  Block to_in{};
+  std::vector<Level> levels;
+
+  ~OnsetEncoder() { for (void* p : owned) cudaFree(p); }
+  int fail(int code, const char* fmt, ...) {
+    char b[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(b, sizeof b, fmt, ap);
+    va_end(ap);
+    err = b;
+    return code;
+  }
+  float* up(const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = params.find(name);
+    if (it == params.end()) { fail(SFB_ERR_MISSING, "missing encoder parameter '%s'", name.c_str()); return nullptr; }
+    if (it->second.shape != std::vector<int64_t>(shape)) { fail(SFB_ERR_INVALID, "encoder parameter '%s' has the wrong shape", name.c_str()); return nullptr; }
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(it->second.v.size() * 4, 16)) != cudaSuccess) { fail(SFB_ERR_CUDA, "cudaMalloc"); return nullptr; }
+    owned.push_back(d);
+    if (cudaMemcpy(d, it->second.v.data(), it->second.v.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { fail(SFB_ERR_CUDA, "cudaMemcpy"); return nullptr; }
+    return reinterpret_cast<float*>(d);
+  }
+  bool load_block(const std::string& pre, int cin, int cout, int groups, Block& b) {
+    b.cin = cin; b.cout = cout;
+    b.g1 = (cin % groups == 0) ? groups : 1;      // ResnetBlock1d: block1 falls back to one group when cin is not divisible
+    b.g2 = groups;
+    b.gn1_w = up(pre + "block1.groupnorm.weight", {cin}); b.gn1_b = up(pre + "block1.groupnorm.bias", {cin});
+    b.c1_w = up(pre + "block1.project.weight", {cout, cin, 3}); b.c1_b = up(pre + "block1.project.bias", {cout});
+    b.gn2_w = up(pre + "block2.groupnorm.weight", {cout}); b.gn2_b = up(pre + "block2.groupnorm.bias", {cout});
+    b.c2_w = up(pre + "block2.project.weight", {cout, cout, 3}); b.c2_b = up(pre + "block2.project.bias", {cout});
+    b.sc_w = b.sc_b = nullptr;
+    if (cin != cout) { b.sc_w = up(pre + "to_out.weight", {cout, cin, 1}); b.sc_b = up(pre + "to_out.bias", {cout}); }
+    return b.gn1_w && b.gn1_b && b.c1_w && b.c1_b && b.gn2_w && b.gn2_b && b.c2_w && b.c2_b && (cin == cout || (b.sc_w && b.sc_b));
+  }
+  int finalize() {
+    if (finalized) return SFB_OK;
+    const sfb_encoder_config& c = cfg;
+    if (c.patch_size != 1) return fail(SFB_ERR_UNSUPPORTED, "patch_size must be 1 (exp/model/diffusion.yaml:43)");
+    if (c.n_levels < 1 || c.n_levels > SFB_MAX_DEPTH) return fail(SFB_ERR_INVALID, "n_levels out of range");
+    if (!load_block("to_in.", c.in_channels, c.channels * c.multipliers[0], 1, to_in)) return err.empty() ? SFB_ERR_MISSING : SFB_ERR_MISSING;
+    levels.resize(c.n_levels);
+    for (int i = 0; i < c.n_levels; ++i) {
+      Level& lv = levels[i];
+      lv.cin = c.channels * c.multipliers[i]; lv.cout = c.channels * c.multipliers[i + 1]; lv.f = c.factors[i];
+      if (lv.cout > kEncMaxC || lv.cin > kEncMaxC) return fail(SFB_ERR_UNSUPPORTED, "encoder channels > %d", kEncMaxC);
+      if (lv.cout % c.resnet_groups) return fail(SFB_ERR_UNSUPPORTED, "channels not divisible by resnet_groups");
+      const std::string pre = "downsamples." + std::to_string(i) + ".";
+      lv.dw = up(pre + "downsample.weight", {lv.cout, lv.cin, 2 * lv.f + 1}); lv.db = up(pre + "downsample.bias", {lv.cout});
+      if (!lv.dw || !lv.db) return SFB_ERR_MISSING;
+      lv.blocks.resize(c.num_blocks[i]);
+      for (int j = 0; j < c.num_blocks[i]; ++j)
+        if (!load_block(pre + "blocks." + std::to_string(j) + ".", lv.cout, lv.cout, c.resnet_groups, lv.blocks[j])) return SFB_ERR_MISSING;
+    }
+    params.clear();
+    finalized = true;
+    return SFB_OK;
+  }
+  int64_t level_len(int64_t L, int i) const {      // output length of level i (Conv1d k = 2f+1, stride f, padding f)
+    int64_t l = L;
+    for (int k = 0; k <= i; ++k) l = (l + 2 * cfg.factors[k] - (2 * cfg.factors[k] + 1)) / cfg.factors[k] + 1;
+    return l;
+  }
+  int n_gn() const { int n = 2; for (const Level& lv : levels) n += 2 * (int)lv.blocks.size(); return n; }
+  size_t stats_bytes(int64_t B) const { return (size_t)n_gn() * B * 8 * 2 * sizeof(double); }
+  size_t buf_floats(int64_t B, int64_t L) const {
+    size_t m = (size_t)to_in.cout * L;
+    for (int i = 0; i < (int)levels.size(); ++i) m = std::max(m, (size_t)levels[i].cout * level_len(L, i));
+    return align_up(m * B, 256);
+  }
+  size_t workspace_bytes(int64_t B, int64_t L) const { return align_up(stats_bytes(B), 1024) + 4 * buf_floats(B, L) * sizeof(float) + 1024; }
+
+  void conv(cudaStream_t st, const float* in, int Cin, int64_t Lin, const float* w, const float* bias, float* out, int Cout, int64_t Lout,
+            int K, int stride, int pad, const double* gn_stats, int G, const float* gw, const float* gb, const float* res, int Cres,
+            const float* sc_w, const float* sc_b, double* out_stats, int Gout, int64_t B) {
+    EncConvParams p;
+    p.in = in; p.w = w; p.bias = bias; p.out = out; p.gn_stats = gn_stats; p.gn_w = gw; p.gn_b = gb; p.res = res; p.sc_w = sc_w; p.sc_b = sc_b;
+    p.out_stats = out_stats; p.G = G; p.Gout = Gout; p.Cin = Cin; p.Cout = Cout; p.Cres = Cres; p.Lin = (int)Lin; p.Lout = (int)Lout;
+    p.K = K; p.stride = stride; p.pad = pad; p.eps = 1e-5f;
+    enc_conv_kernel<<<dim3((unsigned)((Lout + 127) / 128), (unsigned)Cout, (unsigned)B), 128, 0, st>>>(p);
+  }
+  // X [B, cin, L] with statistics sX (g1 groups) -> out [B, cout, L]; next_stats / next_G: statistics the consumer needs
+  void resnet(cudaStream_t st, const Block& b, const float* X, const double* sX, float* H, double* sH, float* out, double* next_stats,
+              int next_G, int64_t L, int64_t B) {
+    conv(st, X, b.cin, L, b.c1_w, b.c1_b, H, b.cout, L, 3, 1, 1, sX, b.g1, b.gn1_w, b.gn1_b, nullptr, 0, nullptr, nullptr, sH, b.g2, B);
+    conv(st, H, b.cout, L, b.c2_w, b.c2_b, out, b.cout, L, 3, 1, 1, sH, b.g2, b.gn2_w, b.gn2_b, X, b.cin, b.sc_w, b.sc_b, next_stats, next_G, B);
+  }
+  int forward(const float* y, int64_t B, int64_t L, float* const* xs_out, int n_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!finalized) return fail(SFB_ERR_STATE, "finalize first");
+    if (n_out != (int)levels.size() + 1) return fail(SFB_ERR_INVALID, "xs_out needs %d tensors (to_in output + one per level)", (int)levels.size() + 1);
+    if (B <= 0 || L <= 0 || L > INT32_MAX / 4) return fail(SFB_ERR_INVALID, "bad B / L");
+    if (!ws || ws_bytes < workspace_bytes(B, L)) return fail(SFB_ERR_INVALID, "encoder workspace too small");
+    uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 1024));
+    double* stats = reinterpret_cast<double*>(base);
+    float* buf = reinterpret_cast<float*>(base + align_up(stats_bytes(B), 1024));
+    const size_t bf = buf_floats(B, L);
+    float *A = buf, *H = buf + bf, *R0 = buf + 2 * bf, *R1 = buf + 3 * bf;
+    if (cudaMemsetAsync(stats, 0, stats_bytes(B), st) != cudaSuccess) return fail(SFB_ERR_CUDA, "memset");
+    int si = 0;
+    auto next_stats = [&]() { return stats + (size_t)(si++) * B * 16; };
+    // to_in = ResnetBlock1d(in_channels -> channels * m0, one group)
+    double* sY = next_stats();
+    enc_stats_kernel<<<dim3((unsigned)((L + 1023) / 1024), (unsigned)cfg.in_channels, (unsigned)B), 256, 0, st>>>(y, sY, cfg.in_channels, (int)L, to_in.g1);
+    resnet(st, to_in, y, sY, H, next_stats(), xs_out[0], nullptr, 1, L, B);
+    const float* cur = xs_out[0];
+    int64_t Lc = L;
+    for (int i = 0; i < (int)levels.size(); ++i) {
+      const Level& lv = levels[i];
+      const int64_t Lo = level_len(L, i);
+      const int nb = (int)lv.blocks.size();
+      float* dst0 = nb == 0 ? xs_out[i + 1] : A;
+      double* s_in = nb ? next_stats() : nullptr;
+      conv(st, cur, lv.cin, Lc, lv.dw, lv.db, dst0, lv.cout, Lo, 2 * lv.f + 1, lv.f, lv.f, nullptr, 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+           s_in, nb ? lv.blocks[0].g1 : 1, B);
+      const float* x = dst0;
+      for (int j = 0; j < nb; ++j) {
+        const bool last = j == nb - 1;
+        float* out = last ? xs_out[i + 1] : ((j & 1) ? R1 : R0);
+        double* sH = next_stats();
+        double* s_next = last ? nullptr : next_stats();
+        resnet(st, lv.blocks[j], x, s_in, H, sH, out, s_next, last ? 1 : lv.blocks[j + 1].g1, Lo, B);
+        x = out; s_in = s_next;
+      }
+      cur = xs_out[i + 1]; Lc = Lo;
+    }
+    return cudaGetLastError() == cudaSuccess ? SFB_OK : fail(SFB_ERR_CUDA, "encoder launch: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+};
+
 // Fault injection for the wait log: one warp waits on a barrier nobody ever arrives on (tests/test_gpu_waitlog.py).
 struct FaultParams { int tag; };
 #undef SFB_FILE_ID
 #define SFB_FILE_ID 9
 __global__ void wait_fault_kernel(const __grid_constant__ FaultParams p) {
   __shared__ __align__(8) uint64_t bar;
+  mark_progress(p.tag);
   if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
   __syncthreads();
   mbar_wait(&bar, 0);
@@ -1734,6 +1925,105 @@ int sfb_dbg_profile_report(sfb_handle* h, char* buf, int buf_len) {
 int sfb_dbg_sk_timeline(sfb_handle* h, int op_index, long long* host_buf, int n) {
   if (!h) return SFB_ERR_INVALID;
   return h->e->sk_timeline(op_index, host_buf, n);
+}
+struct sfb_encoder { OnsetEncoder e; };
+
+int sfb_encoder_create(const sfb_encoder_config* cfg, int device, sfb_encoder** out) {
+  if (!cfg || !out) return SFB_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SFB_ERR_CUDA;   // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return SFB_ERR_CUDA;
+  sfb_encoder* h = new sfb_encoder();
+  h->e.cfg = *cfg;
+  h->e.device = device;
+  *out = h;
+  return SFB_OK;
+}
+void sfb_encoder_destroy(sfb_encoder* h) { delete h; }
+const char* sfb_encoder_last_error(const sfb_encoder* h) { return h ? h->e.err.c_str() : "null handle"; }
+int sfb_encoder_set_param(sfb_encoder* h, const char* name, const void* data, const int64_t* shape, int ndim) {
+  if (!h || !name || !data || !shape || ndim < 0 || ndim > 4) return SFB_ERR_INVALID;
+  if (h->e.finalized) return h->e.fail(SFB_ERR_STATE, "already finalized");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.v.resize(n);
+  if (cudaMemcpy(t.v.data(), data, n * sizeof(float), cudaMemcpyDefault) != cudaSuccess) return h->e.fail(SFB_ERR_CUDA, "set_param(%s) copy failed", name);
+  h->e.params[name] = std::move(t);
+  return SFB_OK;
+}
+int sfb_encoder_finalize(sfb_encoder* h) {
+  if (!h) return SFB_ERR_INVALID;
+  cudaSetDevice(h->e.device);
+  return h->e.finalize();
+}
+int64_t sfb_encoder_level_length(sfb_encoder* h, int64_t L, int level) {
+  if (!h || level < -1 || level >= h->e.cfg.n_levels) return -1;
+  return level < 0 ? L : h->e.level_len(L, level);
+}
+int sfb_encoder_workspace_bytes(sfb_encoder* h, int64_t B, int64_t L, size_t* out) {
+  if (!h || !out) return SFB_ERR_INVALID;
+  if (!h->e.finalized) return h->e.fail(SFB_ERR_STATE, "finalize first");
+  *out = h->e.workspace_bytes(B, L);
+  return SFB_OK;
+}
+int sfb_encoder_forward(sfb_encoder* h, const float* y, int64_t B, int64_t L, float* const* xs_out, int n_out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  if (!h) return SFB_ERR_INVALID;
+  if (!y || !xs_out) return h->e.fail(SFB_ERR_INVALID, "null argument");
+  if (cudaSetDevice(h->e.device) != cudaSuccess) return h->e.fail(SFB_ERR_CUDA, "cudaSetDevice failed");
+  return h->e.forward(y, B, L, xs_out, n_out, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int64_t sfb_postprocess_out_len(int64_t cut_length, int orig_freq, int new_freq) {
+  if (cut_length <= 0 || orig_freq <= 0 || new_freq < 0) return -1;
+  if (new_freq == 0 || new_freq == orig_freq) return cut_length;
+  const int g = std::gcd(orig_freq, new_freq);
+  const int64_t o = orig_freq / g, n = new_freq / g;
+  return (n * cut_length + o - 1) / o;       // ceil(new * length / orig), torchaudio's target_length
+}
+
+int sfb_postprocess(int device, const float* gen, const float* onsets, int64_t B, int64_t L, int64_t cut_length, int orig_freq,
+                    int new_freq, float* out, int64_t out_len, int* first_onset, void* stream) {
+  if (!gen || !out || B <= 0 || L <= 0 || cut_length <= 0 || cut_length > L || orig_freq <= 0 || new_freq < 0) return SFB_ERR_INVALID;
+  if (onsets && !first_onset) return SFB_ERR_INVALID;
+  if (L > INT32_MAX / 2) return SFB_ERR_UNSUPPORTED;
+  if (out_len != sfb_postprocess_out_len(cut_length, orig_freq, new_freq)) return SFB_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return SFB_ERR_CUDA;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (onsets) {
+    fill_int_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(first_onset, (int)B, (int)L);
+    first_onset_kernel<<<dim3((unsigned)((L / 4 + 256) / 256), (unsigned)B), 256, 0, st>>>(onsets, first_onset, (int)L);
+  }
+  PostParams p;
+  p.gen = gen; p.first_onset = onsets ? first_onset : nullptr; p.table = nullptr; p.out = out;
+  p.L = (int)L; p.cut = (int)cut_length; p.T = (int)out_len; p.orig = p.nw = p.K = p.width = 0; p.fpb = 1;
+  if (new_freq == 0 || new_freq == orig_freq) {
+    postprocess_copy_kernel<<<dim3((unsigned)std::min<int64_t>((out_len + 1023) / 1024, 4096), (unsigned)B), 256, 0, st>>>(p);
+  } else {
+    const ResampleTable* t = resample_table(device, orig_freq, new_freq);
+    if (!t) return SFB_ERR_CUDA;
+    p.table = t->dev; p.orig = t->orig; p.nw = t->nw; p.K = t->K; p.width = t->width;
+    const int max_floats = 40 * 1024;                                // 160 KB of shared memory for the staged span
+    if (t->K > max_floats) return SFB_ERR_UNSUPPORTED;              // rate pairs with a huge reduced orig_freq
+    p.fpb = std::max(1, std::min(8, (max_floats - t->K) / t->orig + 1));
+    const size_t smem = (size_t)((p.fpb - 1) * t->orig + t->K) * sizeof(float);
+    static std::mutex mu;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (cudaFuncSetAttribute(postprocess_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(max_floats * sizeof(float))) != cudaSuccess)
+        return SFB_ERR_CUDA;
+    }
+    const int64_t frames = (out_len + t->nw - 1) / t->nw;
+    postprocess_resample_kernel<<<dim3((unsigned)((frames + p.fpb - 1) / p.fpb), (unsigned)B), 256, smem, st>>>(p);
+  }
+  return cudaGetLastError() == cudaSuccess ? SFB_OK : SFB_ERR_CUDA;
+}
+
+int sfb_dbg_set_grid_limit(sfb_handle* h, int max_ctas) {
+  if (!h || max_ctas < 0) return SFB_ERR_INVALID;
+  g_grid_limit = max_ctas;
+  return SFB_OK;
 }
 int sfb_dbg_wait_log(sfb_handle* h, char* buf, int buf_len) {
   if (!h || !buf || buf_len <= 0) return SFB_ERR_INVALID;

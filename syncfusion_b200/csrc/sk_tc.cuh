@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
   tc_fence_before();
   __syncthreads();
   pdl_wait();            // everything above is independent of the previous kernel's output
+  mark_progress(p.tag);
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) SK_STAMP(7, 0);

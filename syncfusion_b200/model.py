@@ -242,6 +242,10 @@ class UNetV0:
         self._lib.sfb_dbg_wait_log(self._h, buf, len(buf))
         return buf.value.decode(errors="replace")
 
+    def debug_set_grid_limit(self, max_ctas: int):
+        """Persistent kernels use at most ``max_ctas`` CTAs (0: one per SM) - more tiles per CTA for the ring tests."""
+        self._check(self._lib.sfb_dbg_set_grid_limit(self._h, int(max_ctas)))
+
     def debug_set_op_limit(self, n: int):
         self._check(self._lib.sfb_dbg_set_op_limit(self._h, int(n)))
 
