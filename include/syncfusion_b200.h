@@ -76,6 +76,11 @@ int sfb_finalize(sfb_handle* h);
 /* Bytes of caller-owned device workspace needed for batch B, length L, CFG on/off and up to `rows` conditioning
  * rows (num_steps + 1 for sample, B for a free-standing net call). */
 int sfb_workspace_bytes(sfb_handle* h, int64_t B, int64_t L, int cfg_on, int64_t rows, size_t* out);
+/* Same for an embedding of M context tokens (1 <= M <= embedding_max_length, M <= 128).  M = 1 (the shipped
+ * embedding_max_length: 1, main/module_diffusion.py:67,71) needs no extra space: the cross-attention items collapse to
+ * per-clip bias vectors.  M > 1 runs the general CrossAttentionItem (LayerNorm -> q projection -> attention over the M
+ * keys -> output projection) and adds the q / attention-output / k|v buffers. */
+int sfb_workspace_bytes_m(sfb_handle* h, int64_t B, int64_t L, int cfg_on, int64_t rows, int64_t M, size_t* out);
 
 /* net(x, time, embedding=, embedding_scale=, channels=) -> v      (inner boundary)
  *   x [B,1,L] f32, sigma [B] f32, channels[d] [B, ctx_d, L_d] f32 (NCL as the reference passes them),
@@ -141,6 +146,7 @@ int sfb_dbg_set_op_limit(sfb_handle* h, int n_ops);
 /* Number of plan ops for (B, L, cfg_on) and a one-line description of op i:
  * "kind depth stack item out_offset out_bytes rows cols dtype". */
 int sfb_dbg_plan_size(sfb_handle* h, int64_t B, int64_t L, int cfg_on, void* workspace, size_t workspace_bytes);
+int sfb_dbg_plan_size_m(sfb_handle* h, int64_t B, int64_t L, int cfg_on, int64_t M, void* workspace, size_t workspace_bytes);
 int sfb_dbg_op_info(sfb_handle* h, int i, char* buf, int buf_len);
 /* Launch the persistent kernels (streaming-K / resident-weight / generic GEMM) with at most `max_ctas` CTAs (0: one per
  * SM).  Process-wide.  Fewer CTAs = more tiles per CTA: the parity tests use it to drive the shared-memory rings, the

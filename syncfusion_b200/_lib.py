@@ -11,9 +11,9 @@ LIB_PATH = Path(os.environ["SFB_LIB"]) if os.environ.get("SFB_LIB") else HERE / 
 SFB_MAX_DEPTH = 16
 
 EXPORTS = [
-    "sfb_create", "sfb_destroy", "sfb_last_error", "sfb_set_param", "sfb_finalize", "sfb_workspace_bytes",
+    "sfb_create", "sfb_destroy", "sfb_last_error", "sfb_set_param", "sfb_finalize", "sfb_workspace_bytes", "sfb_workspace_bytes_m",
     "sfb_unet_forward", "sfb_sample", "sfb_last_launch_count", "sfb_postprocess", "sfb_postprocess_out_len", "sfb_encoder_create", "sfb_encoder_destroy", "sfb_encoder_last_error",
-    "sfb_encoder_set_param", "sfb_encoder_finalize", "sfb_encoder_level_length", "sfb_encoder_workspace_bytes", "sfb_encoder_forward", "sfb_dbg_set_op_limit", "sfb_dbg_plan_size",
+    "sfb_encoder_set_param", "sfb_encoder_finalize", "sfb_encoder_level_length", "sfb_encoder_workspace_bytes", "sfb_encoder_forward", "sfb_dbg_set_op_limit", "sfb_dbg_plan_size", "sfb_dbg_plan_size_m",
     "sfb_dbg_op_info", "sfb_dbg_wait_log", "sfb_dbg_fault_inject", "sfb_dbg_set_grid_limit", "sfb_dbg_sk_timeline", "sfb_dbg_profile", "sfb_dbg_profile_report", "sfb_dbg_gemm", "sfb_dbg_attention",
 ]
 
@@ -63,6 +63,8 @@ def load() -> C.CDLL:
     lib.sfb_set_param.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32]
     lib.sfb_finalize.argtypes = [vp]
     lib.sfb_workspace_bytes.argtypes = [vp, i64, i64, i32, i64, C.POINTER(C.c_size_t)]
+    if hasattr(lib, "sfb_workspace_bytes_m"):
+        lib.sfb_workspace_bytes_m.argtypes = [vp, i64, i64, i32, i64, i64, C.POINTER(C.c_size_t)]
     lib.sfb_unet_forward.argtypes = [vp, vp, vp, C.POINTER(vp), i32, vp, i64, f32, vp, i64, i64, vp, C.c_size_t, vp]
     lib.sfb_sample.argtypes = [vp, vp, i32, C.POINTER(vp), i32, vp, i64, f32, vp, vp, vp, vp, i64, i64, vp,
                                C.c_size_t, vp]
@@ -86,6 +88,8 @@ def load() -> C.CDLL:
     lib.sfb_last_launch_count.restype = i64
     lib.sfb_dbg_set_op_limit.argtypes = [vp, i32]
     lib.sfb_dbg_plan_size.argtypes = [vp, i64, i64, i32, vp, C.c_size_t]
+    if hasattr(lib, "sfb_dbg_plan_size_m"):
+        lib.sfb_dbg_plan_size_m.argtypes = [vp, i64, i64, i32, i64, vp, C.c_size_t]
     lib.sfb_dbg_op_info.argtypes = [vp, i32, C.c_char_p, i32]
     lib.sfb_dbg_sk_timeline.argtypes = [vp, i32, vp, i32]
     if hasattr(lib, "sfb_dbg_set_grid_limit"):
@@ -98,7 +102,7 @@ def load() -> C.CDLL:
     lib.sfb_dbg_gemm.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.sfb_dbg_attention.argtypes = [i32, vp, vp, i32, i32, vp]
     for name in EXPORTS:          # every symbol the header declares must resolve
-        if os.environ.get("SFB_LIB") and (name in ("sfb_dbg_wait_log", "sfb_dbg_fault_inject", "sfb_dbg_set_grid_limit", "sfb_postprocess", "sfb_postprocess_out_len") or name.startswith("sfb_encoder_")) and not hasattr(lib, name):
+        if os.environ.get("SFB_LIB") and (name in ("sfb_dbg_wait_log", "sfb_dbg_fault_inject", "sfb_dbg_set_grid_limit", "sfb_postprocess", "sfb_postprocess_out_len", "sfb_workspace_bytes_m", "sfb_dbg_plan_size_m") or name.startswith("sfb_encoder_")) and not hasattr(lib, name):
             continue
         getattr(lib, name)
     _lib = lib

@@ -24,7 +24,10 @@ struct AttnParams {
   CUtensorMap tmKV;   // same tensor, box [atom, BKV, 1]
   CUtensorMap tmV;    // same box; bf16: identical to tmKV, tf32: 128B swizzle with 32-byte atoms (MN-major tf32)
   T* out;             // [B, N, 512]
-  int n_tokens;
+  int n_tokens;       // query tokens N
+  int kv_tokens;      // key / value tokens (= N for self-attention; M_ctx for cross-attention, a9 / a10)
+  int q_col0, k_col0, v_col0;   // first column of q / k / v in their tensors (self: 0 / 512 / 1024 of one [.., 1536] tensor;
+                                // cross: q in a [.., 512] tensor, k | v in a [.., 1024] tensor)
   float scale_log2;   // log2(e) / sqrt(64)
   int tag;            // plan op index (wait log)
 };
@@ -39,7 +42,7 @@ __device__ __forceinline__ float fast_exp2(float x) {   // single MUFU.EX2
   return y;
 }
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;      // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
 constexpr int kHeadDim = 64;
 
 template <typename T>
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
   constexpr int kQBytes = DA * 128 * 128;
   constexpr int kKBytes = DA * BKV * 128;
   constexpr int kPBytes = PA * 128 * 128;
-  constexpr uint32_t kTmemCols = 256;           // S: [0, BKV), O_j: [BKV, BKV + 64)
+  constexpr uint32_t kTmemCols = 256;           // S: [0, BKV), O: [BKV, BKV + 64), then 6 exchange columns
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int nkv = (p.n_tokens + BKV - 1) / BKV;
+  const int nkv = (p.kv_tokens + BKV - 1) / BKV;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -88,9 +91,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 256);
     mbar_init(o_full, 1);
-    mbar_init(s_free, 128);
+    mbar_init(s_free, 256);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -105,15 +108,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------- TMA producer
     mbar_expect_tx(q_full, kQBytes);
-    for (int a = 0; a < DA; ++a) tma_load_3d(sQ + a * 128 * 128, &p.tmQ, q_full, h * kHeadDim + a * AE, q0, b);
+    for (int a = 0; a < DA; ++a) tma_load_3d(sQ + a * 128 * 128, &p.tmQ, q_full, p.q_col0 + h * kHeadDim + a * AE, q0, b);
     for (int j = 0; j < nkv; ++j) {
       const int s = j & 1;
       mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
       mbar_expect_tx(&kv_full[s], 2 * kKBytes);
       uint8_t* sk = sKV + s * 2 * kKBytes;
       for (int a = 0; a < DA; ++a) {
-        tma_load_3d(sk + a * BKV * 128, &p.tmKV, &kv_full[s], 512 + h * kHeadDim + a * AE, j * BKV, b);
-        tma_load_3d(sk + kKBytes + a * BKV * 128, &p.tmV, &kv_full[s], 1024 + h * kHeadDim + a * AE, j * BKV, b);
+        tma_load_3d(sk + a * BKV * 128, &p.tmKV, &kv_full[s], p.k_col0 + h * kHeadDim + a * AE, j * BKV, b);
+        tma_load_3d(sk + kKBytes + a * BKV * 128, &p.tmV, &kv_full[s], p.v_col0 + h * kHeadDim + a * AE, j * BKV, b);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -166,118 +169,147 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
       umma_commit(&kv_empty[s]);
     }
   } else if (warp >= 2) {
-    // ------------------------------------------------------------- softmax (one query row per thread)
+    // ------------------------------------------------------------- softmax: TWO threads per query row
+    // Warps 2-5 take key columns [0, BKV/2) of their TMEM lane quarter, warps 6-9 columns [BKV/2, BKV) of the same
+    // quarter (a warp may only touch lanes 32 (warp % 4) ...).  Four softmax warps per scheduler (two CTAs per SM)
+    // instead of two: the MUFU.EX2 stream of one warp overlaps the TMEM loads, row-max chains and P stores of the
+    // others (r1: 44 % MUFU utilisation with one thread per row), and 64 instead of 128 score registers per thread end
+    // the spills.  The partners agree on the row max through two spare TMEM columns per tile parity (shared memory is
+    // full at two CTAs per SM) and on the row sum once at the end.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
+    constexpr int HC = BKV / 2;                    // score columns per thread
+    constexpr int OC = kHeadDim / 2;               // output columns per thread
     const uint32_t lane_off = uint32_t(q * 32) << 16;
+    const uint32_t tmem_X = tmem_base + BKV + kHeadDim + lane_off;     // exchange columns: [2 tile parities][2 halves] max, then [2] sums
+    auto pair_sync = [&]() {                       // named barrier of this warp pair (64 threads), id = 1 + q as an immediate
+      if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+      else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+      else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+      else asm volatile("bar.sync 4, 64;" ::: "memory");
+    };
     float m_used = -INFINITY, l_run = 0.f;
     const float sc = p.scale_log2;
     for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(BKV, p.n_tokens - j * BKV);
+      const int kv_valid = min(BKV, p.kv_tokens - j * BKV);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t v[BKV];
+      uint32_t v[HC];
 #pragma unroll
-      for (int c = 0; c < BKV; c += 32) tmem_ld32(tmem_S + lane_off + c, v + c);
+      for (int c = 0; c < HC; c += 32) tmem_ld32(tmem_S + lane_off + half * HC + c, v + c);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(s_free);                       // the S columns may be overwritten by S(j+1)
       if (kv_valid != BKV) {                     // tile-uniform: only the last tile of a ragged sequence is masked
 #pragma unroll
-        for (int i = 0; i < BKV; ++i)
-          if (i >= kv_valid) v[i] = 0xFF800000u;   // -inf
+        for (int i = 0; i < HC; ++i)
+          if (half * HC + i >= kv_valid) v[i] = 0xFF800000u;   // -inf
       }
       float mx0 = __uint_as_float(v[0]), mx1 = __uint_as_float(v[1]);
 #pragma unroll
-      for (int i = 2; i < BKV; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1])); }
-      const float mx = fmaxf(mx0, mx1);
+      for (int i = 2; i < HC; i += 2) { mx0 = fmaxf(mx0, __uint_as_float(v[i])); mx1 = fmaxf(mx1, __uint_as_float(v[i + 1])); }
+      float mx = fmaxf(mx0, mx1);
+      {   // row max over both halves
+        const uint32_t xc = tmem_X + 2 * (j & 1);
+        tmem_st1(xc + half, __float_as_uint(mx));
+        tmem_st_wait();
+        tc_fence_before();
+        pair_sync();
+        tc_fence_after();
+        const uint32_t other = tmem_ld1(xc + (half ^ 1));
+        tmem_ld_wait();
+        mx = fmaxf(mx, __uint_as_float(other));
+      }
       // lazy running max: rescale only when this row's max grew by more than 2^8 relative to the max in use
+      // (both partners see the same mx and m_used, so they take the same branch)
       const bool need = (mx - m_used) * sc > 8.f;             // true on the first tile (m_used = -inf)
       bool o_waited = false;
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? ((m_used == -INFINITY) ? 0.f : exp2f((m_used - mx) * sc)) : 1.f;
         if (need) m_used = mx;
         l_run *= alpha;
-        if (j > 0) {               // O(j-1) is complete: read - scale - write back (whole warp, per-lane factor)
+        if (j > 0) {               // O(j-1) is complete: read - scale - write back this thread's half of the row
           mbar_wait(o_full, (j - 1) & 1);
           tc_fence_after();
           o_waited = true;
+          uint32_t o[OC];
+          tmem_ld32(tmem_O + lane_off + half * OC, o);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < kHeadDim; c += 32) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + lane_off + c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem_O + lane_off + c, o);
-          }
+          for (int i = 0; i < OC; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_O + lane_off + half * OC, o);
           tmem_st_wait();
         }
       }
       const float moff = m_used * sc;
       float rs0 = 0.f, rs1 = 0.f;
-      // probabilities in place (fp32), row sum on the un-rounded values (two independent chains); the operand-precision
-      // rounding of P is zero-mean, so the normaliser differs from sum(round(P)) by ~1e-4 relative at most.
+      // probabilities (fp32), row sum on the un-rounded values (two independent chains); the operand-precision rounding
+      // of P is zero-mean, so the normaliser differs from sum(round(P)) by ~1e-4 relative at most.  The packed values
+      // go to their OWN register array: packing in place (v[i / 2] = pack(v[i], v[i + 1])) demoted v[] to local memory.
+      constexpr int PW = sizeof(T) == 2 ? HC / 2 : HC;        // 32-bit words of this thread's P half row
+      uint32_t pk[PW];
 #pragma unroll
-      for (int i = 0; i < BKV; i += 2) {
+      for (int i = 0; i < HC; i += 2) {
         const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, -moff)), p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -moff));
         rs0 += p0; rs1 += p1;
         if constexpr (sizeof(T) == 2) {
           __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-          v[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);       // packed pair i/2 (slots below i are already consumed)
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         } else {
-          v[i] = __float_as_uint(from_f32<float>(p0)); v[i + 1] = __float_as_uint(from_f32<float>(p1));
+          pk[i] = __float_as_uint(from_f32<float>(p0)); pk[i + 1] = __float_as_uint(from_f32<float>(p1));
         }
       }
       l_run += rs0 + rs1;
       if (j > 0 && !o_waited) mbar_wait(o_full, (j - 1) & 1);   // P V(j-1) no longer reads the P tile
-      // write this row's probabilities into the swizzled K-major P tile (operand precision)
-      if constexpr (sizeof(T) == 2) {
+      // this thread's half row of the swizzled K-major P tile (operand precision): exactly one 128-byte atom row
+      {
+        uint8_t* prow = sP + half * 128 * 128 + r * 128;
 #pragma unroll
-        for (int ch = 0; ch < BKV / 8; ++ch) {    // 16-byte chunks of 8 keys; 8 chunks per 128-byte atom row
-          const int atom = ch / 8, cc = ch % 8;
-          uint4* dst = reinterpret_cast<uint4*>(sP + atom * 128 * 128 + r * 128 + ((cc ^ (r & 7)) * 16));
-          *dst = make_uint4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int ch = 0; ch < BKV / 4; ++ch) {    // 16-byte chunks of 4 keys; 8 chunks per 128-byte atom row (32 keys)
-          const int atom = ch / 8, cc = ch % 8;
-          uint4* dst = reinterpret_cast<uint4*>(sP + atom * 128 * 128 + r * 128 + ((cc ^ (r & 7)) * 16));
-          *dst = make_uint4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
-        }
+        for (int cc = 0; cc < 8; ++cc)
+          *reinterpret_cast<uint4*>(prow + ((cc ^ (r & 7)) * 16)) = make_uint4(pk[cc * 4], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
       }
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(p_ready);
     }
-    // O is complete in TMEM: normalise and store
+    // O is complete in TMEM: combine the two half-row sums, normalise and store this thread's half of the head
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
+    {
+      const uint32_t xc = tmem_X + 4;
+      tmem_st1(xc + half, __float_as_uint(l_run));
+      tmem_st_wait();
+      tc_fence_before();
+      pair_sync();
+      tc_fence_after();
+      const uint32_t other = tmem_ld1(xc + (half ^ 1));
+      tmem_ld_wait();
+      l_run += __uint_as_float(other);
+    }
     const float inv = 1.f / l_run;
     const bool valid = q0 + r < p.n_tokens;
-    T* dst = p.out + ((size_t)b * p.n_tokens + q0 + r) * 512 + h * kHeadDim;
-#pragma unroll
-    for (int c = 0; c < kHeadDim; c += 32) {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_off + c, o);
+    T* dst = p.out + ((size_t)b * p.n_tokens + q0 + r) * 512 + h * kHeadDim + half * OC;
+    {
+      uint32_t o[OC];
+      tmem_ld32(tmem_O + lane_off + half * OC, o);
       tmem_ld_wait();
       if (valid) {
         if constexpr (sizeof(T) == 2) {
 #pragma unroll
-          for (int c8 = 0; c8 < 32; c8 += 8) {
+          for (int c8 = 0; c8 < OC; c8 += 8) {
             uint32_t w[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(o[c8 + 2 * t]) * inv, __uint_as_float(o[c8 + 2 * t + 1]) * inv);
               w[t] = *reinterpret_cast<uint32_t*>(&h2);
             }
-            *reinterpret_cast<uint4*>(dst + c + c8) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst + c8) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         } else {
 #pragma unroll
-          for (int c4 = 0; c4 < 32; c4 += 4)
-            *reinterpret_cast<float4*>(dst + c + c4) =
+          for (int c4 = 0; c4 < OC; c4 += 4)
+            *reinterpret_cast<float4*>(dst + c4) =
                 make_float4(__uint_as_float(o[c4]) * inv, __uint_as_float(o[c4 + 1]) * inv, __uint_as_float(o[c4 + 2]) * inv,
                             __uint_as_float(o[c4 + 3]) * inv);
         }

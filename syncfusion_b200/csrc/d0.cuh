@@ -434,4 +434,52 @@ __global__ void __launch_bounds__(256, 3) d0_tail_kernel(const T* __restrict__ h
   if (stats_out) d0_flush_stats(sm, fa, fq, stats_out + (size_t)b * 16);
 }
 
+
+// Depth-0 output projection of the general cross-attention item (a10, M_ctx > 1; C = 8 is below every tensor-core tile):
+//   out[b, l, c] = x[b, l, c] + sum_k o[b, l, k] Wo[c, k]      o [B, L, 512] operand precision, Wo [8][512] f32
+// + operand copy and GroupNorm sums of the output (group = channel at C = 8).  One position per thread, Wo in smem.
+template <typename T>
+__global__ void __launch_bounds__(256) xattn_out_c8_kernel(const T* __restrict__ o, const float* __restrict__ wo, const float* resid,
+                                                           float* out_r, T* __restrict__ out_t, double* __restrict__ stats, int L) {
+  pdl_trigger();
+  __shared__ float sw[8 * 512];
+  __shared__ Stats8Smem sm;
+  for (int i = threadIdx.x; i < 8 * 512; i += 256) sw[i] = wo[i];
+  pdl_wait();
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int l = blockIdx.x * 256 + threadIdx.x;
+  const bool valid = l < L;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    const T* row = o + ((size_t)b * L + l) * 512;
+    for (int k = 0; k < 512; k += 8) {
+      float x[8];
+      if constexpr (sizeof(T) == 2) {
+        const uint4 u = *reinterpret_cast<const uint4*>(row + k);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { x[2 * j] = __uint_as_float(w[j] << 16); x[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(row + k), c = *reinterpret_cast<const float4*>(row + k + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c] = fmaf(x[j], sw[c * 512 + k + j], acc[c]);
+    }
+    const size_t g = ((size_t)b * L + l) * 8;
+    const float4 r0 = *reinterpret_cast<const float4*>(resid + g), r1 = *reinterpret_cast<const float4*>(resid + g + 4);
+    acc[0] += r0.x; acc[1] += r0.y; acc[2] += r0.z; acc[3] += r0.w; acc[4] += r1.x; acc[5] += r1.y; acc[6] += r1.z; acc[7] += r1.w;
+    *reinterpret_cast<float4*>(out_r + g) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(out_r + g + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    if (out_t != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out_t[g + c] = from_f32<T>(acc[c]);
+    }
+  }
+  if (stats != nullptr) stats8_block_reduce(acc, valid, stats + (size_t)b * 16, sm);
+}
+
 }  // namespace sfb

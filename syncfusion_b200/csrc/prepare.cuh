@@ -80,11 +80,18 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   for (int k = lane; k < C; k += 32) out[(size_t)r * C + k] = (ir[k] - mean) * rstd * gamma[k] + beta[k];
 }
 
-// Build the effective embedding rows for the CFG-doubled batch: rows [0, B) = embedding, rows [B, 2B) = fixed row.
+// Effective context rows of the CFG-doubled batch: rows [0, n_cond) = the caller's embedding tokens [B, M, F] as they
+// are, rows [n_cond, ...) = FixedEmbedding token (r - n_cond) % M (the mask branch of ClassifierFreeGuidancePlugin, A.4).
 __global__ void build_emb_rows_kernel(const float* __restrict__ emb, const float* __restrict__ fixed, float* __restrict__ out,
-                                      int B, int Beff, int F) {
+                                      int n_cond, int M, int F) {
   const int r = blockIdx.x;
-  for (int k = threadIdx.x; k < F; k += blockDim.x) out[(size_t)r * F + k] = (r < B) ? emb[(size_t)r * F + k] : fixed[k];
+  const float* src = r < n_cond ? emb + (size_t)r * F : fixed + (size_t)((r - n_cond) % M) * F;
+  for (int k = threadIdx.x; k < F; k += blockDim.x) out[(size_t)r * F + k] = src[k];
+}
+template <typename T>
+__global__ void __launch_bounds__(256) f32_to_operand_kernel(const float* __restrict__ in, T* __restrict__ out, size_t n) {
+  const size_t i = blockIdx.x * (size_t)256 + threadIdx.x;
+  if (i < n) out[i] = from_f32<T>(in[i]);
 }
 
 

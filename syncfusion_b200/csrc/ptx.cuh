@@ -166,6 +166,7 @@ __device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, uin
 // Every kernel of the per-step chain calls pdl_trigger() first (the NEXT kernel's CTAs may be scheduled as soon as
 // SMs free up and run their prologue) and pdl_wait() before touching global memory (blocks until the PREVIOUS kernel
 // has completed and flushed).  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* g) { asm volatile("prefetch.global.L1 [%0];" ::"l"(g)); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -328,6 +329,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
         "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
         "r"(r[30]), "r"(r[31])
       : "memory");
+}
+// one fp32 column of this warp's 32 lanes (cross-warp exchange of per-row scalars through spare TMEM columns)
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

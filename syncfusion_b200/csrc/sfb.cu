@@ -121,6 +121,10 @@ struct ItemW {
   float *c8_w1 = nullptr, *c8_b1 = nullptr, *c8_w2 = nullptr, *c8_b2 = nullptr, *c8_wi = nullptr, *c8_bi = nullptr;
   bool has_attn = false, has_xattn = false, has_inject = false;
   float *x_ng = nullptr, *x_nb = nullptr, *x_wv = nullptr, *x_wo = nullptr;
+  // general M_ctx > 1 cross-attention (K6): q projection with the query LayerNorm affine folded in, full to_kv, to_out
+  GemmW xq, xout;
+  float* x_wkv = nullptr;
+  int xkv_index = -1;
   int mod_off = 0, xb_off = 0;
   float* qkv_ws = nullptr;   // [1536] column sums of the bf16 fused QKV weights (LayerNorm fold, sk_tc.cuh)
 };
@@ -135,8 +139,8 @@ struct DepthW {
   int skip_off = 0;
 };
 
-enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN, OP_RK, OP_SK, OP_D0_CONV1, OP_D0_TAIL };
-const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn", "rk", "sk", "d0_conv1", "d0_tail"};
+enum OpKind { OP_D0_DOWN = 0, OP_GN, OP_CONV_C8, OP_INJ_C8, OP_D0_UP, OP_GEMM, OP_LN, OP_ATTN, OP_RK, OP_SK, OP_D0_CONV1, OP_D0_TAIL, OP_XOUT_C8 };
+const char* kOpNames[] = {"d0_down", "gn_silu", "conv3_c8", "inject_c8", "d0_up", "gemm", "ln", "attn", "rk", "sk", "d0_conv1", "d0_tail", "xattn_out_c8"};
 
 // ------------------------------------------------------------------------------------------------ wait log (ptx.cuh)
 // One host-mapped log per process: the device writes it when a barrier wait outlasts c_wait_bound (then traps); the
@@ -170,14 +174,14 @@ struct EngineBase {
   int64_t launches = 0;
   virtual ~EngineBase() {}
   virtual int finalize() = 0;
-  virtual int workspace_bytes(int64_t B, int64_t L, int cfg_on, int64_t rows, size_t* out) = 0;
+  virtual int workspace_bytes(int64_t B, int64_t L, int cfg_on, int64_t rows, int64_t M, size_t* out) = 0;
   virtual int unet_forward(const float* x, const float* sigma, const float* const* channels, int n_channels,
                            const float* embedding, int64_t M, float scale, float* v_out, int64_t B, int64_t L, void* ws,
                            size_t ws_bytes, cudaStream_t st) = 0;
   virtual int sample(const float* x_noisy, int num_steps, const float* const* channels, int n_channels,
                      const float* embedding, int64_t M, float scale, float* x_out, float* traj_x, float* traj_v,
                      const float* teacher_x, int64_t B, int64_t L, void* ws, size_t ws_bytes, cudaStream_t st) = 0;
-  virtual int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes) = 0;
+  virtual int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes, int64_t M = 1) = 0;
   virtual int op_info(int i, char* buf, int len) = 0;
   virtual int profile_report(char* buf, int len) = 0;
   virtual int sk_timeline(int op_index, long long* host_buf, int n) { (void)op_index; (void)host_buf; (void)n; return SFB_ERR_UNSUPPORTED; }
@@ -310,7 +314,7 @@ struct Engine : EngineBase {
   // conditioning weights (fp32)
   float *t_w = nullptr, *t_lw = nullptr, *t_lb = nullptr, *t_mw = nullptr, *t_mb = nullptr, *fixed_emb = nullptr;
   float *ft_w = nullptr, *ft_b = nullptr;   // concatenated Linear(SiLU(features)) weights [F_total][MF]
-  int F_total = 0, XB_total = 0, n_gn = 0;
+  int F_total = 0, XB_total = 0, n_gn = 0, n_xattn = 0;
   bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aids: force the unfused generic path
   bool no_sk = getenv("SFB_NO_SK") != nullptr;
   bool no_d0_fused = getenv("SFB_NO_D0_FUSED") != nullptr;
@@ -346,10 +350,12 @@ struct Engine : EngineBase {
     size_t ctx[SFB_MAX_DEPTH], bufA[SFB_MAX_DEPTH], T1[SFB_MAX_DEPTH], T2[SFB_MAX_DEPTH], qkv[SFB_MAX_DEPTH], o[SFB_MAX_DEPTH];
     size_t rs1[SFB_MAX_DEPTH], rs2[SFB_MAX_DEPTH];   // per-position LayerNorm partial sums [rows, parts <= 8, 2] (sk path)
     size_t foldw, foldw_bytes;                        // scaled inject weights + (ws | wsh) vectors, B copies (LayerNorm fold)
+    size_t xln, xq, xo, xkv;                          // general cross-attention (M_ctx > 1): LN(x), q, attention output, per-item k | v
   };
   struct Plan {
     int64_t B = 0, L = 0;
     int cfg_on = 0;
+    int64_t M = 1;            // context tokens of the cross-attention (1: collapsed to a bias)
     void* ws = nullptr;
     WsLayout lay;
     std::vector<Op> ops;
@@ -443,7 +449,7 @@ struct Engine : EngineBase {
 
     std::vector<float> ftw, ftb;   // concatenated feature linears
     dw.assign(D, DepthW());
-    F_total = 0; XB_total = 0;
+    F_total = 0; XB_total = 0; n_xattn = 0;
     for (int d = 0; d < D; ++d) {
       const int C = c.channels[d], Cin = d == 0 ? c.in_channels : c.channels[d - 1], f = c.factors[d], ctx = c.context_channels[d];
       DepthW& W = dw[d];
@@ -663,6 +669,27 @@ struct Engine : EngineBase {
             I.x_ng = upload_f(g); I.x_nb = upload_f(b); I.x_wv = upload<float>(wv); I.x_wo = upload_f(wo);
             I.xb_off = XB_total;
             XB_total += C;
+            if (c.embedding_max_length > 1) {      // general M_ctx path (K6): W_q' = W_q diag(g_q), b_q = W_q beta_q; full to_kv; to_out
+              const HostTensor* wq = get(Q + "xattn.attn.to_q.weight", {mid, C});
+              const HostTensor* gq = get(Q + "xattn.attn.norm.weight", {C});
+              const HostTensor* bq = get(Q + "xattn.attn.norm.bias", {C});
+              std::vector<float> r((size_t)mid * C), bb(mid);
+              for (int n = 0; n < mid; ++n) {
+                double acc = 0;
+                for (int k = 0; k < C; ++k) {
+                  r[(size_t)n * C + k] = wq->v[(size_t)n * C + k] * gq->v[k];
+                  acc += (double)wq->v[(size_t)n * C + k] * bq->v[k];
+                }
+                bb[n] = (float)acc;
+              }
+              I.xq.w = upload_T(r); I.xq.bias = upload<float>(bb);
+              I.xq.N = mid; I.xq.K1 = C; I.xq.taps = 1; I.xq.bias_mod = mid;
+              I.xout.w = upload_T(wo->v); I.xout.bias = nullptr;
+              I.xout.N = C; I.xout.K1 = mid; I.xout.taps = 1; I.xout.bias_mod = C;
+              I.x_wkv = upload_f(wkv);
+              I.xkv_index = n_xattn++;
+              if (!I.xq.w || !I.xq.bias || !I.xout.w || !I.x_wkv) return fail(SFB_ERR_CUDA, "upload failed");
+            }
           }
         }
       }
@@ -683,16 +710,16 @@ struct Engine : EngineBase {
     for (int i = 0; i <= d; ++i) f *= cfg.factors[i];
     return (int)(L / f);
   }
-  void layout(int64_t B, int64_t L, int cfg_on, int64_t rows, WsLayout& w) const {
+  void layout(int64_t B, int64_t L, int cfg_on, int64_t rows, int64_t M, WsLayout& w) const {
     const int64_t Beff = cfg_on ? 2 * B : B;
     const int MF = cfg.modulation_features, EF = cfg.embedding_features;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
     const int64_t R = std::max<int64_t>(rows, 1);
     w.sigma = take(R * 4);
-    w.embrows = take(Beff * EF * 4);
-    w.tmp1 = take(Beff * EF * 4);
-    w.tmp2 = take(Beff * EF * 4);
+    w.embrows = take(Beff * M * EF * 4);
+    w.tmp1 = take(Beff * M * EF * 4);
+    w.tmp2 = take(Beff * M * std::max(EF, 1024) * 4);
     w.fourier = take(R * 257 * 4);
     w.h1 = take(R * MF * 4);
     w.h2 = take(R * MF * 4);
@@ -700,7 +727,7 @@ struct Engine : EngineBase {
     w.ftable = take(R * (size_t)F_total * 4);
     w.xbias = take(Beff * (size_t)std::max(XB_total, 1) * 4);
     int ngn = 0;
-    for (int d = 0; d < cfg.depth; ++d) ngn += 4 * cfg.items[d] + 2;
+    for (int d = 0; d < cfg.depth; ++d) ngn += (M > 1 ? 6 : 4) * cfg.items[d] + 2;
     w.stats_bytes = (size_t)ngn * Beff * 16 * sizeof(double);
     w.stats = take(w.stats_bytes);
     w.veff = take(Beff * L * 4);
@@ -730,19 +757,30 @@ struct Engine : EngineBase {
           for (const ItemW& I : dw[d].items[s])
             w.foldw_bytes += fold_item_bytes(I, B);
     w.foldw = take(std::max<size_t>(w.foldw_bytes, 16));
+    w.xln = w.xq = w.xo = w.xkv = 0;
+    if (M > 1) {
+      size_t lc = 0;
+      for (int d = 0; d < cfg.depth; ++d) lc = std::max(lc, (size_t)Ld(L, d) * cfg.channels[d]);
+      w.xln = take((size_t)Beff * lc * sizeof(T));
+      w.xq = take((size_t)Beff * L * 512 * sizeof(T));
+      w.xo = take((size_t)Beff * L * 512 * sizeof(T));
+      w.xkv = take((size_t)std::max(n_xattn, 1) * Beff * M * 1024 * sizeof(T));
+    }
     w.total = off;
   }
   // scaled weight copies [B][N][K] bf16 + vectors [B][2 N] fp32 of one streaming-K inject item
   static size_t fold_w_bytes(const ItemW& I, int64_t copies) { return align_up((size_t)copies * I.inject.N * (I.inject.K1 + I.inject.K2) * 2, 1024); }
   static size_t fold_item_bytes(const ItemW& I, int64_t copies) { return fold_w_bytes(I, copies) + align_up((size_t)copies * 2 * I.inject.N * 4, 1024); }
-  int workspace_bytes(int64_t B, int64_t L, int cfg_on, int64_t rows, size_t* out) override {
+  int workspace_bytes(int64_t B, int64_t L, int cfg_on, int64_t rows, int64_t M, size_t* out) override {
+    if (M < 1 || M > cfg.embedding_max_length) return fail(SFB_ERR_INVALID, "embedding length M=%lld must be in [1, embedding_max_length=%d]", (long long)M, cfg.embedding_max_length);
+    if (M > 128) return fail(SFB_ERR_UNSUPPORTED, "cross-attention context longer than 128 tokens");
     if (!finalized) return fail(SFB_ERR_STATE, "finalize first");
     int64_t tf = 1;
     for (int d = 0; d < cfg.depth; ++d) tf *= cfg.factors[d];
     if (B <= 0 || L <= 0 || L % tf) return fail(SFB_ERR_INVALID, "L=%lld must be a positive multiple of %lld", (long long)L, (long long)tf);
     if (L % 8) return fail(SFB_ERR_INVALID, "L must be a multiple of 8");
     WsLayout w;
-    layout(B, L, cfg_on, rows, w);
+    layout(B, L, cfg_on, rows, M, w);
     *out = w.total + 1024;
     return SFB_OK;
   }
@@ -859,6 +897,51 @@ struct Engine : EngineBase {
     if (d + 1 < cfg.depth && !sk_ok(dw[d + 1].up)) return false;
     return true;
   }
+  // General cross-attention item (a10, K6; M_ctx > 1): x + W_o softmax(q k^T / 8) v with q = W_q LN(x) (query LayerNorm
+  // affine folded into W_q), k | v = to_kv(LN_ctx(e)) precomputed per call.  Four ops behind the item's last op:
+  // LayerNorm pass -> q projection (tcgen05 GEMM) -> attention core (the self-attention kernel with its own K/V source
+  // and a masked partial key tile) -> output projection + residual (+ operand copy and GroupNorm sums for the consumer).
+  int append_xattn(int d, int s, int i, const ItemW& I, float* A, void* out_t, double* stats_out) {
+    const int Beff = plan.cfg_on ? 2 * (int)plan.B : (int)plan.B;
+    const int C = cfg.channels[d], L = Ld(plan.L, d), gs = C / 8, rows = Beff * L, M = (int)plan.M;
+    T* XLN = at<T>(plan.lay.xln);
+    T* XQ = at<T>(plan.lay.xq);
+    T* XO = at<T>(plan.lay.xo);
+    T* KV = at<T>(plan.lay.xkv) + (size_t)I.xkv_index * Beff * M * 1024;
+    auto base = [&](int kind, const char* ck) { Op o; o.kind = kind; o.depth = d; o.stack = s; o.item = i; o.L = L; o.C = C; o.gs = gs; o.B = Beff; o.ck = ck; return o; };
+    {
+      Op o = base(OP_LN, "xattn_ln"); o.in = A; o.out_t = XLN; o.out_r = nullptr; o.ft_off = -1;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    {
+      Op o = base(OP_GEMM, "xattn_q"); o.out_t = XQ;
+      if (!add_gemm(o, I.xq, XLN, C, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (xattn q d%d)", d);
+      set_dbg(o, rows, 512); plan.ops.push_back(o);
+    }
+    {
+      Op o = base(OP_ATTN, "xattn"); o.in = XQ; o.out_t = XO;
+      constexpr int AE = ElemTraits<T>::kAtomElems;
+      if (!make_tmap3<T>(&o.ap.tmQ, XQ, 512, L, Beff, AE, 128) ||
+          !make_tmap3<T>(&o.ap.tmKV, KV, 1024, M, Beff, AE, AttnCfg<T>::BKV) ||
+          !make_tmap3<T>(&o.ap.tmV, KV, 1024, M, Beff, AE, AttnCfg<T>::BKV,
+                         sizeof(T) == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return fail(SFB_ERR_CUDA, "tensor map encode failed (cross-attention d%d)", d);
+      o.ap.out = XO; o.ap.n_tokens = L; o.ap.kv_tokens = M; o.ap.q_col0 = 0; o.ap.k_col0 = 0; o.ap.v_col0 = 512;
+      o.ap.scale_log2 = 1.4426950408889634f / 8.0f;
+      set_dbg(o, rows, 512); plan.ops.push_back(o);
+    }
+    if (d == 0) {
+      Op o = base(OP_XOUT_C8, "xattn_out"); o.in = XO; o.w0 = I.x_wo; o.resid = A; o.out_r = A; o.out_t = out_t; o.stats_out = stats_out;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    } else {
+      Op o = base(OP_GEMM, "xattn_out"); o.resid = A; o.out_r = A; o.out_t = out_t; o.stats_out = stats_out;
+      if (!add_gemm(o, I.xout, XO, 512, L, Beff, nullptr, 0)) return fail(SFB_ERR_CUDA, "tensor map encode failed (xattn out d%d)", d);
+      o.gp.gs = gs;
+      set_dbg(o, rows, C); plan.ops.push_back(o);
+    }
+    return SFB_OK;
+  }
+
   int build_item_sk(int d, int s, int i, double*& cur, bool want_stats) {
     const int64_t B = plan.B;
     const int Beff = plan.cfg_on ? 2 * (int)B : (int)B;
@@ -871,7 +954,7 @@ struct Engine : EngineBase {
     float* RS2 = at<float>(plan.lay.rs2[d]);
     void* P0 = xt_cur[d];
     void* P1 = (P0 == (void*)T1) ? (void*)T2 : (void*)T1;
-    const float* xb = I.has_xattn ? at<float>(plan.lay.xbias) + I.xb_off : nullptr;
+    const float* xb = (I.has_xattn && plan.M == 1) ? at<float>(plan.lay.xbias) + I.xb_off : nullptr;   // M = 1: collapsed to a bias
     auto base = [&](const char* ck) { Op o; o.kind = OP_SK; o.depth = d; o.stack = s; o.item = i; o.L = L; o.C = C; o.gs = gs; o.B = Beff; o.ck = ck; return o; };
     const int rows = Beff * L;
     double* sB = new_stats(Beff);
@@ -936,7 +1019,7 @@ struct Engine : EngineBase {
             !make_tmap3<T>(&o.ap.tmV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV,
                            sizeof(T) == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
           return fail(SFB_ERR_CUDA, "tensor map encode failed (attention d%d)", d);
-        o.ap.out = O; o.ap.n_tokens = L; o.ap.scale_log2 = 1.4426950408889634f / 8.0f;
+        o.ap.out = O; o.ap.n_tokens = L; o.ap.kv_tokens = L; o.ap.q_col0 = 0; o.ap.k_col0 = 512; o.ap.v_col0 = 1024; o.ap.scale_log2 = 1.4426950408889634f / 8.0f;
         set_dbg(o, rows, 512); plan.ops.push_back(o);
       }
       {  // out projection + residual (+ cross-attention bias)  ->  bufA (fp32), P0 (bf16), GroupNorm sums
@@ -950,6 +1033,12 @@ struct Engine : EngineBase {
     }
     item_t_out = xt_cur[d];
     cur = sOut;
+    if (I.has_xattn && plan.M > 1) {      // the consumer reads the bf16 copy in xt_cur[d] and the statistics in `cur`
+      double* sX = want_stats ? new_stats(Beff) : nullptr;
+      int rc = append_xattn(d, s, i, I, A, xt_cur[d], sX);
+      if (rc) return rc;
+      cur = sX;
+    }
     return SFB_OK;
   }
 
@@ -964,7 +1053,7 @@ struct Engine : EngineBase {
     float* A = at<float>(plan.lay.bufA[d]);
     T* T1 = at<T>(plan.lay.T1[d]);
     T* T2 = at<T>(plan.lay.T2[d]);
-    const float* xb = I.has_xattn ? at<float>(plan.lay.xbias) + I.xb_off : nullptr;
+    const float* xb = (I.has_xattn && plan.M == 1) ? at<float>(plan.lay.xbias) + I.xb_off : nullptr;   // M = 1: collapsed to a bias
     auto base = [&](int kind, const char* ck) { Op o; o.kind = kind; o.depth = d; o.stack = s; o.item = i; o.L = L; o.C = C; o.gs = gs; o.B = Beff; o.ck = ck; return o; };
     const int rows = Beff * L;
     const bool last_is_inject = !I.has_attn;
@@ -1075,7 +1164,7 @@ struct Engine : EngineBase {
             !make_tmap3<T>(&o.ap.tmV, QKV, 1536, L, Beff, AE, AttnCfg<T>::BKV,
                            sizeof(T) == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
           return fail(SFB_ERR_CUDA, "tensor map encode failed (attention d%d)", d);
-        o.ap.out = O; o.ap.n_tokens = L; o.ap.scale_log2 = 1.4426950408889634f / 8.0f;
+        o.ap.out = O; o.ap.n_tokens = L; o.ap.kv_tokens = L; o.ap.q_col0 = 0; o.ap.k_col0 = 512; o.ap.v_col0 = 1024; o.ap.scale_log2 = 1.4426950408889634f / 8.0f;
         set_dbg(o, rows, 512); plan.ops.push_back(o);
       }
       {
@@ -1087,6 +1176,12 @@ struct Engine : EngineBase {
       }
     }
     cur = sOut;
+    if (I.has_xattn && plan.M > 1) {
+      double* sX = want_stats ? new_stats(Beff) : nullptr;
+      int rc = append_xattn(d, s, i, I, A, want_t ? item_t_out : nullptr, sX);
+      if (rc) return rc;
+      cur = sX;
+    }
     return SFB_OK;
   }
 
@@ -1240,6 +1335,9 @@ struct Engine : EngineBase {
       } else if (o.kind == OP_D0_TAIL) {
         flops = 2.0 * rows * 8 * (24 + 8 + o.ctx);
         bytes = rows * (8 * (sizeof(T) + 4 + 4 + (o.out_t ? sizeof(T) : 0)) + o.ctx * sizeof(T));
+      } else if (o.kind == OP_XOUT_C8) {
+        flops = 2.0 * rows * 8 * 512;
+        bytes = rows * (512 * sizeof(T) + 8 * (4 + 4 + (o.out_t ? sizeof(T) : 0)));
       } else if (o.kind == OP_D0_DOWN) {
         flops = 2.0 * rows * 8;
         bytes = rows * (4 + 32);
@@ -1301,20 +1399,20 @@ struct Engine : EngineBase {
     return out;
   }
 
-  int ensure_plan(int64_t B, int64_t L, int cfg_on, int64_t rows, void* ws, size_t ws_bytes) {
+  int ensure_plan(int64_t B, int64_t L, int cfg_on, int64_t rows, void* ws, size_t ws_bytes, int64_t M = 1) {
     if (!finalized) return fail(SFB_ERR_STATE, "finalize first");
     size_t need = 0;
-    int rc = workspace_bytes(B, L, cfg_on, rows, &need);
+    int rc = workspace_bytes(B, L, cfg_on, rows, M, &need);
     if (rc) return rc;
     if (!ws || ws_bytes < need) return fail(SFB_ERR_INVALID, "workspace too small: %zu < %zu", ws_bytes, need);
     uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(ws), 1024));
     WsLayout lay;
-    layout(B, L, cfg_on, rows, lay);
-    if (plan.ws == base && plan.B == B && plan.L == L && plan.cfg_on == cfg_on && plan.lay.total == lay.total &&
+    layout(B, L, cfg_on, rows, M, lay);
+    if (plan.ws == base && plan.B == B && plan.L == L && plan.cfg_on == cfg_on && plan.M == M && plan.lay.total == lay.total &&
         !plan.ops.empty())
       return SFB_OK;
     plan = Plan();
-    plan.B = B; plan.L = L; plan.cfg_on = cfg_on; plan.ws = base; plan.lay = lay;
+    plan.B = B; plan.L = L; plan.cfg_on = cfg_on; plan.M = M; plan.ws = base; plan.lay = lay;
     wsb = base;
     stats_next = 0;
     fold_items.clear(); fold_next = 0; fold_rows = 0;
@@ -1349,8 +1447,8 @@ struct Engine : EngineBase {
     }
     return SFB_OK;
   }
-  int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes) override {
-    int rc = ensure_plan(B, L, cfg_on, B, ws, ws_bytes);
+  int plan_size(int64_t B, int64_t L, int cfg_on, void* ws, size_t ws_bytes, int64_t M = 1) override {
+    int rc = ensure_plan(B, L, cfg_on, B, ws, ws_bytes, M);
     if (rc) return rc;
     return (int)plan.ops.size();
   }
@@ -1484,6 +1582,10 @@ struct Engine : EngineBase {
           else launch_ln<4>(o, sc, st);
           break;
         }
+        case OP_XOUT_C8:
+          launch_pdl(xattn_out_c8_kernel<T>, dim3(lb, o.B), 256, 0, st, reinterpret_cast<const T*>(o.in), o.w0, o.resid, o.out_r,
+                     reinterpret_cast<T*>(o.out_t), o.stats_out, o.L);
+          break;
         case OP_ATTN: {
           dim3 grid((o.L + 127) / 128, 8, o.B);
           launch_pdl(attn_tc_kernel<T>, grid, kAttnThreads, attn_smem_bytes<T>(), st, o.ap);
@@ -1503,7 +1605,7 @@ struct Engine : EngineBase {
     const int64_t B = plan.B, L = plan.L;
     const int Beff = plan.cfg_on ? 2 * (int)B : (int)B;
     const int MF = cfg.modulation_features, EF = cfg.embedding_features;
-    if (M != 1) return fail(SFB_ERR_UNSUPPORTED, "embedding length M=%lld: only the M_ctx = 1 path is implemented (embedding_max_length: 1)", (long long)M);
+    if (M != plan.M) return fail(SFB_ERR_STATE, "plan was built for M=%lld", (long long)plan.M);
     if (n_channels < cfg.depth) return fail(SFB_ERR_INVALID, "channels: need %d context tensors, got %d", cfg.depth, n_channels);
     if (!embedding) return fail(SFB_ERR_INVALID, "embedding is required (ClassifierFreeGuidancePlugin)");
     const WsLayout& w = plan.lay;
@@ -1520,9 +1622,26 @@ struct Engine : EngineBase {
     lin(at<float>(w.h2), t_mw, t_mb, at<float>(w.feat), rows, MF, MF, MF, ACT_NONE, ACT_GELU);
     lin(at<float>(w.feat), ft_w, ft_b, at<float>(w.ftable), rows, MF, F_total, F_total, ACT_SILU, ACT_NONE);
     // cross-attention biases (A.4 + A.7, M_ctx = 1)
-    build_emb_rows_kernel<<<Beff, 128, 0, st>>>(embedding, fixed_emb, at<float>(w.embrows), (int)B, Beff, EF);
+    // rows [0, B*M) = the caller's embedding tokens, rows [B*M, 2*B*M) = FixedEmbedding tokens 0..M-1 (CFG mask branch)
+    build_emb_rows_kernel<<<(unsigned)(Beff * M), 128, 0, st>>>(embedding, fixed_emb, at<float>(w.embrows), (int)(B * M), (int)M, EF);
     ++launches;
-    for (int d = 0; d < cfg.depth; ++d)
+    if (M > 1) {
+      // general cross-attention: k | v = to_kv(LN_ctx(e)) per item, [Beff, M, 1024] in operand precision (loop invariant)
+      const int R2 = (int)(Beff * M);
+      for (int d = 0; d < cfg.depth; ++d)
+        for (int s = 0; s < 2; ++s)
+          for (const ItemW& I : dw[d].items[s]) {
+            if (!I.has_xattn) continue;
+            if (I.xkv_index < 0) return fail(SFB_ERR_STATE, "cross-attention weights for M > 1 were not built (embedding_max_length = %d)", cfg.embedding_max_length);
+            ln_rows_kernel<<<(R2 + 7) / 8, 256, 0, st>>>(at<float>(w.embrows), I.x_ng, I.x_nb, at<float>(w.tmp1), R2, EF, 1e-5f);
+            ++launches;
+            lin(at<float>(w.tmp1), I.x_wkv, nullptr, at<float>(w.tmp2), R2, EF, 1024, 1024, ACT_NONE, ACT_NONE);
+            const size_t n = (size_t)R2 * 1024;
+            f32_to_operand_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(at<float>(w.tmp2), at<T>(w.xkv) + (size_t)I.xkv_index * n, n);
+            ++launches;
+          }
+    }
+    for (int d = 0; d < cfg.depth && M == 1; ++d)
       for (int s = 0; s < 2; ++s)
         for (const ItemW& I : dw[d].items[s]) {
           if (!I.has_xattn) continue;
@@ -1546,7 +1665,7 @@ struct Engine : EngineBase {
                    int64_t M, float scale, float* v_out, int64_t B, int64_t L, void* ws, size_t ws_bytes,
                    cudaStream_t st) override {
     const int cfg_on = scale != 1.0f;
-    int rc = ensure_plan(B, L, cfg_on, B, ws, ws_bytes);
+    int rc = ensure_plan(B, L, cfg_on, B, ws, ws_bytes, M);
     if (rc) return rc;
     wsb = reinterpret_cast<uint8_t*>(plan.ws);
     launches = 0;
@@ -1567,7 +1686,7 @@ struct Engine : EngineBase {
              void* ws, size_t ws_bytes, cudaStream_t st) override {
     if (num_steps <= 0) return fail(SFB_ERR_INVALID, "num_steps must be positive");
     const int cfg_on = scale != 1.0f;
-    int rc = ensure_plan(B, L, cfg_on, num_steps + 1, ws, ws_bytes);
+    int rc = ensure_plan(B, L, cfg_on, num_steps + 1, ws, ws_bytes, M);
     if (rc) return rc;
     wsb = reinterpret_cast<uint8_t*>(plan.ws);
     launches = 0;
@@ -1827,7 +1946,7 @@ static int dbg_attn_t(const void* qkv, void* out, int B, int N, cudaStream_t st)
       !make_tmap3<T>(&p.tmV, qkv, 1536, N, B, AE, AttnCfg<T>::BKV,
                      sizeof(T) == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
     return SFB_ERR_CUDA;
-  p.out = reinterpret_cast<T*>(out); p.n_tokens = N; p.scale_log2 = 1.4426950408889634f / 8.0f;
+  p.out = reinterpret_cast<T*>(out); p.n_tokens = N; p.kv_tokens = N; p.q_col0 = 0; p.k_col0 = 512; p.v_col0 = 1024; p.scale_log2 = 1.4426950408889634f / 8.0f;
   attn_tc_kernel<T><<<dim3((N + 127) / 128, 8, B), kAttnThreads, attn_smem_bytes<T>(), st>>>(p);
   return cudaGetLastError() == cudaSuccess ? SFB_OK : SFB_ERR_CUDA;
 }
@@ -1879,7 +1998,12 @@ int sfb_finalize(sfb_handle* h) {
 
 int sfb_workspace_bytes(sfb_handle* h, int64_t B, int64_t L, int cfg_on, int64_t rows, size_t* out) {
   if (!h || !out) return SFB_ERR_INVALID;
-  return h->e->workspace_bytes(B, L, cfg_on, rows, out);
+  return h->e->workspace_bytes(B, L, cfg_on, rows, 1, out);
+}
+
+int sfb_workspace_bytes_m(sfb_handle* h, int64_t B, int64_t L, int cfg_on, int64_t rows, int64_t M, size_t* out) {
+  if (!h || !out) return SFB_ERR_INVALID;
+  return h->e->workspace_bytes(B, L, cfg_on, rows, M, out);
 }
 
 int sfb_unet_forward(sfb_handle* h, const float* x, const float* sigma, const float* const* channels, int n_channels,
@@ -1912,6 +2036,10 @@ int sfb_dbg_set_op_limit(sfb_handle* h, int n_ops) {
 int sfb_dbg_plan_size(sfb_handle* h, int64_t B, int64_t L, int cfg_on, void* workspace, size_t workspace_bytes) {
   if (!h) return SFB_ERR_INVALID;
   return h->e->plan_size(B, L, cfg_on, workspace, workspace_bytes);
+}
+int sfb_dbg_plan_size_m(sfb_handle* h, int64_t B, int64_t L, int cfg_on, int64_t M, void* workspace, size_t workspace_bytes) {
+  if (!h) return SFB_ERR_INVALID;
+  return h->e->plan_size(B, L, cfg_on, workspace, workspace_bytes, M);
 }
 int sfb_dbg_profile(sfb_handle* h, int enable) {
   if (!h) return SFB_ERR_INVALID;

@@ -118,10 +118,13 @@ class UNetV0:
         self._finalized = True
         return self
 
-    def _workspace(self, B: int, L: int, cfg_on: int, rows: int) -> Tensor:
+    def _workspace(self, B: int, L: int, cfg_on: int, rows: int, M: int = 1) -> Tensor:
         n = C.c_size_t()
-        self._check(self._lib.sfb_workspace_bytes(self._h, B, L, cfg_on, rows, C.byref(n)))
-        key = (B, L, cfg_on)
+        if M == 1 or not hasattr(self._lib, "sfb_workspace_bytes_m"):
+            self._check(self._lib.sfb_workspace_bytes(self._h, B, L, cfg_on, rows, C.byref(n)))
+        else:
+            self._check(self._lib.sfb_workspace_bytes_m(self._h, B, L, cfg_on, rows, M, C.byref(n)))
+        key = (B, L, cfg_on, M)
         ws = self._ws.get(key)
         if ws is None or ws.numel() < n.value:
             self._ws.clear()                          # one live workspace at a time
@@ -161,7 +164,7 @@ class UNetV0:
         assert time.numel() == B, "time must be [B]"
         emb = embedding.to(device=self.device, dtype=torch.float32).contiguous()
         cfg_on = int(float(embedding_scale) != 1.0)
-        ws = self._workspace(B, L, cfg_on, B)
+        ws = self._workspace(B, L, cfg_on, B, emb.shape[1])
         out = torch.empty_like(x)
         cp = (C.c_void_p * len(chans))(*[c.data_ptr() for c in chans])
         with torch.cuda.device(self.device):
@@ -180,7 +183,7 @@ class UNetV0:
         x = x_noisy.to(device=self.device, dtype=torch.float32).contiguous()
         emb = embedding.to(device=self.device, dtype=torch.float32).contiguous()
         cfg_on = int(float(embedding_scale) != 1.0)
-        ws = self._workspace(B, L, cfg_on, num_steps + 1)
+        ws = self._workspace(B, L, cfg_on, num_steps + 1, emb.shape[1])
         out = torch.empty_like(x)
         tx = tv = None
         if return_trajectory:
@@ -205,9 +208,10 @@ class UNetV0:
         return int(self._lib.sfb_last_launch_count(self._h))
 
     # ------------------------------------------------------------------ test hooks
-    def debug_ops(self, B: int, L: int, cfg_on: int):
-        ws = self._workspace(B, L, cfg_on, B)
-        n = self._lib.sfb_dbg_plan_size(self._h, B, L, cfg_on, self._ptr(ws), ws.numel())
+    def debug_ops(self, B: int, L: int, cfg_on: int, M: int = 1):
+        ws = self._workspace(B, L, cfg_on, B, M)
+        n = (self._lib.sfb_dbg_plan_size(self._h, B, L, cfg_on, self._ptr(ws), ws.numel()) if M == 1 else
+             self._lib.sfb_dbg_plan_size_m(self._h, B, L, cfg_on, M, self._ptr(ws), ws.numel()))
         if n < 0:
             self._check(n)
         ops = []

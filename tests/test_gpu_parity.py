@@ -258,3 +258,66 @@ def test_batch_independence_and_determinism(dev):
     assert rel_l2(one, full[1:2]) < 1e-5
     again = m.sample(x_noisy=x, num_steps=3, channels=ch, embedding=e, embedding_scale=2.0)
     assert rel_l2(again, full) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ general cross-attention
+def _build_xattn(dev, precision, xscale):
+    """Stress init, with the cross-attention q / kv projections rescaled by `xscale` (stress_init_ multiplies them by 4)."""
+    import syncfusion_b200 as sf
+    cfgk = dict(SMALL, embedding_max_length=4)
+    om = make_oracle(cfgk, stress=True)
+    with torch.no_grad():
+        for name, prm in om.net.named_parameters():
+            if ".xattn." in name and name.endswith(("to_q.weight", "to_kv.weight")):
+                prm.mul_(xscale)
+    m = sf.DiffusionModel(sf.UNetConfig(precision=precision, **cfgk), dev)
+    m.load_state_dict(om.net.state_dict())
+    return om, m
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("M,scale", [(4, 1.0), (4, 2.0), (2, 2.0), (1, 2.0)])
+def test_cross_attention_general_context_length(dev, precision, M, scale):
+    """a10 / K6: CrossAttentionItem with M_ctx > 1 context tokens (embedding_max_length = 4) at every depth - d0 (C = 8,
+    CUDA-core projection), the resident-weight depths, the streaming-K depth and the self-attention depth - vs the oracle,
+    inside the un-relaxed bounds (stress init everywhere, cross-attention projections at their default scale); M = 1 under
+    the same configuration still takes the collapsed path."""
+    om, m = _build_xattn(dev, precision, 0.25)
+    om = om.to(dev)
+    B, L = 2, 1024
+    x, ch, _ = _inputs(om, B, L, dev)
+    g = torch.Generator().manual_seed(M)
+    e = torch.randn(B, M, 512, generator=g)
+    e = (e / e.norm(dim=-1, keepdim=True)).to(dev)
+    t = torch.tensor([0.7, 0.3], device=dev)
+    v_ref = om.net(x, t, embedding=e, embedding_scale=scale, channels=ch)
+    v = m.net(x, t, embedding=e, embedding_scale=scale, channels=ch)
+    assert rel_l2(v, v_ref) < TOL_V[precision] * (2.5 if scale != 1.0 else 1.0)
+    ref = om.sample(x, num_steps=4, channels=ch, embedding=e, embedding_scale=scale)
+    out = m.sample(x_noisy=x, num_steps=4, channels=ch, embedding=e, embedding_scale=scale)
+    assert rel_l2(out, ref) < (1e-2 if precision == "fp32" else 5e-2)
+    kinds = [op["ck"] for op in m.net.debug_ops(B, L, int(scale != 1.0), M)[0]]
+    assert ("xattn" in kinds) == (M > 1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cross_attention_sharp_softmax_is_precision_limited(dev, precision):
+    """With the cross-attention projections also scaled x4 the softmax over the context tokens is nearly one-hot and the
+    problem is ill conditioned: the fp32 oracle itself moves 3e-6 against an fp64 evaluation at M = 4 (2e-7 at M = 1),
+    growing ~3.6x per doubling of M.  The CUDA path's error must stay a constant multiple of that conditioning - the
+    operand epsilon ratio tf32 : fp32 (2^-11 : 2^-24, measured ~850x; bf16 ~6700x) - i.e. no error beyond operand
+    rounding (tools/xattn_probe.py prints the table)."""
+    om, m = _build_xattn(dev, precision, 1.0)
+    om64 = make_oracle(dict(SMALL, embedding_max_length=4), stress=True).double().to(dev)
+    om = om.to(dev)
+    B, L, M = 2, 1024, 4
+    x, ch, _ = _inputs(om, B, L, dev)
+    g = torch.Generator().manual_seed(M)
+    e = torch.randn(B, M, 512, generator=g)
+    e = (e / e.norm(dim=-1, keepdim=True)).to(dev)
+    t = torch.tensor([0.7, 0.3], device=dev)
+    v_ref = om.net(x, t, embedding=e, embedding_scale=1.0, channels=ch)
+    v64 = om64.net(x.double(), t.double(), embedding=e.double(), embedding_scale=1.0, channels=[c.double() for c in ch])
+    v = m.net(x, t, embedding=e, embedding_scale=1.0, channels=ch)
+    cond = rel_l2(v_ref, v64)                       # fp32 round-off amplified by the problem's conditioning
+    assert rel_l2(v, v64) < cond * (2500 if precision == "fp32" else 20000)
