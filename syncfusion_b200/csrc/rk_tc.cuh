@@ -145,13 +145,27 @@ struct RkCfg {
   static constexpr int EPI_WARP0 = XF ? 6 : 2;
   static constexpr int TMEM_NEED = EPI == 2 ? 3 * N : 2 * N;
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  // CTAs per SM.  The depth-1 items (C = 32) are bound by the serial chain of their single epilogue warpgroup (wait
+  // accumulator -> TMEM loads -> LayerNorm -> chained MMA round trip -> stage -> fence -> TMA store -> wait for the
+  // store to drain the tile: ~5000 cycles per [128 x 32] tile at 43 % of HBM bandwidth): two independent CTAs per SM
+  // double the tiles in flight with no change to the pipeline protocol (each gets half the ring budget).
+#ifdef SFB_RK_NO_OCC2
+  static constexpr int OCC = 1;
+#else
+  static constexpr int OCC = (K1 == 32 && N == 32 && TAPS == 3 && XF != 0) ? 2 : 1;
+#endif
   // ring depths from the shared-memory budget: these kernels are HBM-latency bound (ncu: every role waits on TMA data at
   // 28 % DRAM utilisation with two A stages), so whatever the resident weights leave goes into bytes in flight.
-  static constexpr int kBudget = 232448 - (W_BYTES + 2 * T_BYTES + A2_BYTES + VEC_FLOATS * 4 + 256 + 1024);
+  static constexpr int kSmemCap = OCC == 2 ? 115712 : 232448;          // 2 x (113 KB + 1 KB reserved) <= 228 KB per SM
+  static constexpr int NT = OCC == 2 ? 1 : 2;    // bf16 staging tiles (one: the store is drained before the next tile is staged)
+  static constexpr int kBudget = kSmemCap - (W_BYTES + NT * T_BYTES + A2_BYTES + VEC_FLOATS * 4 + 256 + 1024);
   static constexpr int PER_A = OP_BYTES + RAW_BYTES;
   static constexpr int PER_R = R_BYTES + CTX_BYTES;
   static constexpr int NSR_FIT = PER_R > 0 ? (kBudget - 2 * PER_A) / PER_R : 3;
-  static constexpr int NSR = NSR_FIT >= 5 ? 5 : (NSR_FIT >= 4 ? 4 : 3);
+  // two residual stages are enough only where a tile's slot goes back to the producer as soon as its own store has
+  // drained it (the chained epilogue, see the end of the tile loop); the other shapes release one tile late
+  static constexpr int NSR_MIN = EPI == 2 ? 2 : 3;
+  static constexpr int NSR = NSR_FIT >= 5 ? 5 : (NSR_FIT >= 4 ? 4 : (NSR_FIT >= 3 ? 3 : NSR_MIN));
   static constexpr int NSA_FIT = (kBudget - NSR * PER_R) / PER_A;
   static constexpr int NSA = NSA_FIT >= 4 ? 4 : (NSA_FIT >= 3 ? 3 : 2);
   // smem carve-up (every tile region is a multiple of 1024 B)
@@ -161,16 +175,16 @@ struct RkCfg {
   static constexpr int OFF_R = OFF_RAW + NSA * RAW_BYTES;
   static constexpr int OFF_CTX = OFF_R + NSR * R_BYTES;
   static constexpr int OFF_T = OFF_CTX + NSR * CTX_BYTES;
-  static constexpr int OFF_A2 = OFF_T + 2 * T_BYTES;
+  static constexpr int OFF_A2 = OFF_T + NT * T_BYTES;
   static constexpr int OFF_VEC = OFF_A2 + A2_BYTES;
   static constexpr int OFF_BAR = OFF_VEC + VEC_FLOATS * 4;
   static constexpr int SMEM = OFF_BAR + 256 + 1024 /*alignment slack*/;
   static_assert(W_BYTES % 1024 == 0 && OP_BYTES % 1024 == 0 && RAW_BYTES % 1024 == 0, "alignment");
-  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(SMEM <= kSmemCap, "shared memory budget");
 };
 
 template <int K1, int N, int TAPS, int XF, int EPI, int BMOD, int USE_R>
-__global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThreads, 1) rk_kernel(const __grid_constant__ RkParams p) {
+__global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThreads, RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::OCC) rk_kernel(const __grid_constant__ RkParams p) {
   pdl_trigger();
   using C = RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>;
   constexpr int NSR = C::NSR;
@@ -224,6 +238,10 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
   if (warp == 1) { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  if (warp == 0 && lane == 0) {      // the resident weights are static: loaded under the previous kernel's tail
+    mbar_expect_tx(w_full, C::W_BYTES);
+    for (int j = 0; j < C::W1_TILES + C::KA2; ++j) tma_load_2d(sW + j * N * 128, &p.tmW, w_full, 0, j * N);
+  }
   pdl_wait();            // everything above is independent of the previous kernel's output
   mark_progress(p.tag);
   tc_fence_after();
@@ -232,8 +250,6 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------- TMA producer
-      mbar_expect_tx(w_full, C::W_BYTES);
-      for (int j = 0; j < C::W1_TILES + C::KA2; ++j) tma_load_2d(sW + j * N * 128, &p.tmW, w_full, 0, j * N);
       uint32_t i = 0;
       for (int t = t_begin; t < t_end; ++t, ++i) {
         const int b = t / p.tiles_per_clip;
@@ -531,7 +547,7 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
       }
       named_bar(2, 128);
       uint8_t* rt = sR + rs * C::R_BYTES;      // fp32 [N/32 atoms][128 rows][128 B], 16-byte chunks XOR-swizzled by row & 7
-      uint8_t* tt = EPI == 2 ? sA2 : sT + s * C::T_BYTES;   // bf16 [N/64 atoms][128 rows][128 B]
+      uint8_t* tt = EPI == 2 ? sA2 : sT + (s % C::NT) * C::T_BYTES;   // bf16 [N/64 atoms][128 rows][128 B]
       if (use_r) mbar_wait(&r_full[rs], (i / NSR) & 1);
       mbar_wait(&acc1_full[s], (i >> 1) & 1);
       tc_fence_after();
@@ -684,9 +700,16 @@ __global__ void __launch_bounds__(RkCfg<K1, N, TAPS, XF, EPI, BMOD, USE_R>::kThr
         if (p.has_out_t)
           for (int a = 0; a < C::TA; ++a) tma_store_3d(&p.tmT, tt + a * 128 * 128, a * 64, l0, b);
         bulk_commit();
-        if (EPI == 2 && p.has_out_t) bulk_wait_read<0>();   // A2 (aliased output copy) is rewritten by the very next tile
-        else bulk_wait_read<1>();                            // tile i-1's stores no longer read their buffers
-        if (use_r && i > 0) mbar_arrive(&r_empty[(i - 1) % NSR]);
+        if (EPI == 2 && p.has_out_t) {
+          bulk_wait_read<0>();                               // A2 (aliased output copy) is rewritten by the very next tile
+          mbar_arrive(&r_empty[rs]);                         // ... and this tile's own residual slot has been drained too
+        } else if (C::NT == 1) {
+          bulk_wait_read<0>();                               // the single staging tile is rewritten by the very next tile
+          if (use_r) mbar_arrive(&r_empty[rs]);
+        } else {
+          bulk_wait_read<1>();                               // tile i-1's stores no longer read their buffers
+          if (use_r && i > 0) mbar_arrive(&r_empty[(i - 1) % NSR]);
+        }
       }
     }
     if (PIPE && pend) finish_tile(p_b, p_l0, p_rs, p_valid, p_i);
@@ -746,10 +769,11 @@ inline cudaError_t rk_set_attrs() {
   return e;
 }
 inline void rk_launch(int id, const RkParams& p, int num_sms, cudaStream_t st) {
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   int i = 0;
 #define X(a, b, c, d, e_, f, g)                                                                                          \
   if (id == i++) {                                                                                                       \
+    const int cap = num_sms * RkCfg<a, b, c, d, e_, f, g>::OCC;                                                          \
+    const int grid = p.total_tiles < cap ? p.total_tiles : cap;                                                          \
     launch_pdl(rk_kernel<a, b, c, d, e_, f, g>, grid, RkCfg<a, b, c, d, e_, f, g>::kThreads, RkCfg<a, b, c, d, e_, f, g>::SMEM, st, p); \
     return;                                                                                                              \
   }

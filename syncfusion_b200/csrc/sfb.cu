@@ -851,6 +851,7 @@ struct Engine : EngineBase {
     if (!make_tmap3<__nv_bfloat16>(&p.tmW, w_override ? w_override : g.w, (uint64_t)(g.K1 + g.K2), (uint64_t)g.taps * g.N,
                                    (uint64_t)w_copies, 64, BN)) return false;
     p.w_bmod = 1;
+    p.w_static = (w_override == nullptr && !getenv("SFB_NO_WPRE")) ? 1 : 0;   // per-evaluation scaled copies are written inside the chain
     p.tmR = p.tmA1; p.tmRs = p.tmA1; p.tmT = p.tmA1;
     p.L = L; p.tiles_per_clip = (L + 127) / 128; p.N = g.N; p.n_tiles = g.N / BN;
     p.total_tiles = Beff * p.tiles_per_clip * p.n_tiles;
@@ -1393,7 +1394,7 @@ struct Engine : EngineBase {
       name_of(off, names, counts, 10);
     } else if (o.kind == OP_ATTN) {
       static const char* const names[] = {"q_full", "kv_full", "kv_empty", "s_full", "p_ready", "o_full", "s_free"};
-      static const int counts[] = {1, 2, 2, 1, 1, 1, 1};
+      static const int counts[] = {1, 4, 4, 1, 1, 1, 1};
       name_of((uint32_t)attn_smem_bytes<T>() - 256, names, counts, 7);
     }
     return out;

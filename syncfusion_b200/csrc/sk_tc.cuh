@@ -9,8 +9,11 @@
 // statistics they need (fp64 group sums per clip, fp32 row sums per position) are emitted by the PRODUCER's epilogue.
 //
 // Persistent, warp-specialised, 128 x BN output tiles (n fastest), fp32 accumulators double-buffered in TMEM:
-//   warp 0      TMA producer (mainloop): A ring of [136 x 64] bf16 tiles - ONE load per K chunk serves all three conv
-//               taps (row-shifted UMMA descriptors, +128 B per tap) - and a B ring of [BN x 64] weight tiles
+//   warp 0      TMA producer (A): ring of [136 x 64] bf16 tiles - ONE load per K chunk serves all three conv taps
+//               (row-shifted UMMA descriptors, +128 B per tap)
+//   warp 3      TMA producer (B): ring of [BN x 64] weight tiles, its own thread so that a full weight ring never holds
+//               back the A loads the transform warps are waiting for; the first ring fill of static weights is issued
+//               before griddepcontrol.wait (it overlaps the previous kernel's tail)
 //   warp 1      tcgen05.mma issuer
 //   warp 2      TMA producer (epilogue): residual chunks [128 x 32] fp32 into the R ring
 //   warps 4-7   A transform in place on the landed tile (fence.proxy.async before the MMA sees it)
@@ -60,6 +63,7 @@ struct SkParams {
   // shared-memory ring depths of this op (host: sk_pick_rings) and the epilogue width
   int na, nb, nr;               // A / weight / residual stages
   int epi12;                    // xf == 0 ops: the four idle A-transform warps join the epilogue (12 warps, three chunk groups)
+  int w_static;                 // the weight tensor is never written inside the launch chain: its first tiles are loaded BEFORE griddepcontrol.wait
   int tag;                      // plan op index (wait log)
   long long* dbg;               // optional timeline buffer (CTA 0 only): [role][256] clock64 stamps (tools/sk_timeline.py)
 };
@@ -154,6 +158,22 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
   if (warp == 3) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
+  // Static weights do not depend on the previous kernel: the first fill of the weight ring (tile t_begin, first k1
+  // chunks) and the GroupNorm affine vectors are requested now, under the previous kernel's tail.
+  int n_pre = 0;
+  if (p.w_static && t_begin < t_end) {
+    const int first_b = p.k1_chunks * p.taps;            // weight tiles of the K1 part of one output tile
+    n_pre = NB < first_b ? NB : first_b;
+    if (warp == 3 && lane == 0) {
+      const int n0 = (t_begin % p.n_tiles) * BN;
+      for (int j = 0; j < n_pre; ++j) {
+        mbar_expect_tx(&b_full[j], C::B_BYTES);
+        tma_load_3d(sB + j * C::B_BYTES, &p.tmW, &b_full[j], (j / p.taps) * 64, (j % p.taps) * p.N + n0, 0);
+      }
+    }
+    if (p.xf == 1 && warp >= 4 && warp < 8)
+      for (int c = (threadIdx.x - 128) * 32; c < p.K1; c += 128 * 32) { prefetch_l1(p.gamma + c); prefetch_l1(p.beta + c); }
+  }
   pdl_wait();            // everything above is independent of the previous kernel's output
   mark_progress(p.tag);
   tc_fence_after();
@@ -162,16 +182,14 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
 
   if (warp == 0) {
     if (lane == 0) {
-      // ------------------------------------------------------------- mainloop TMA producer
-      uint32_t ia = 0, ib = 0;
-      int sa = 0, sb = 0;                 // ring slots and phases advance incrementally (the depths are run-time values:
-      uint32_t pha = 0, phb = 0;          // a division per k chunk on this single thread would cost more than the TMA issue)
+      // ------------------------------------------------------------- mainloop TMA producer: A tiles
+      uint32_t ia = 0;
+      int sa = 0;                         // ring slots and phases advance incrementally (the depths are run-time values:
+      uint32_t pha = 0;                   // a division per k chunk on this single thread would cost more than the TMA issue)
       for (int t = t_begin; t < t_end; ++t) {
-        const int n0 = (t % p.n_tiles) * BN;
         const int mi = t / p.n_tiles;
         const int b = mi / p.tiles_per_clip;
         const int l0 = (mi % p.tiles_per_clip) * 128;
-        const int wcopy = b % p.w_bmod;
         for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc, ++ia) {
           const bool second = kc >= p.k1_chunks;
           mbar_wait(&a_empty[sa], pha ^ 1);
@@ -183,15 +201,32 @@ __global__ void __launch_bounds__(512, 1) sk_kernel(const __grid_constant__ SkPa
             tma_load_3d(sA + sa * C::A_BYTES, &p.tmA2, &a_full[sa], (kc - p.k1_chunks) * 64, l0, b % p.a2_bmod);
           }
           SK_STAMP(0, ia);
+          if (++sa == NA) { sa = 0; pha ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ------------------------------------------------------------- mainloop TMA producer: weight tiles
+      uint32_t ib = 0;
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int n0 = (t % p.n_tiles) * BN;
+        const int b = (t / p.n_tiles) / p.tiles_per_clip;
+        const int wcopy = b % p.w_bmod;
+        for (int kc = 0; kc < p.k1_chunks + p.k2_chunks; ++kc) {
+          const bool second = kc >= p.k1_chunks;
           const int ntap = second ? 1 : p.taps;
           for (int tap = 0; tap < ntap; ++tap, ++ib) {
-            mbar_wait(&b_empty[sb], phb ^ 1);
-            mbar_expect_tx(&b_full[sb], C::B_BYTES);
-            tma_load_3d(sB + sb * C::B_BYTES, &p.tmW, &b_full[sb], second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64, tap * p.N + n0, wcopy);
-            SK_STAMP(1, ib);
+            if (ib >= (uint32_t)n_pre) {             // the first n_pre tiles were issued before griddepcontrol.wait
+              mbar_wait(&b_empty[sb], phb ^ 1);
+              mbar_expect_tx(&b_full[sb], C::B_BYTES);
+              tma_load_3d(sB + sb * C::B_BYTES, &p.tmW, &b_full[sb], second ? p.K1 + (kc - p.k1_chunks) * 64 : kc * 64, tap * p.N + n0, wcopy);
+              SK_STAMP(1, ib);
+            }
             if (++sb == NB) { sb = 0; phb ^= 1; }
           }
-          if (++sa == NA) { sa = 0; pha ^= 1; }
         }
       }
     }

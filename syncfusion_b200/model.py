@@ -341,21 +341,39 @@ class DiffusionModel(torch.nn.Module):
         from .synth import param_shapes
         want = param_shapes(self.cfg)
         got: Dict[str, Tensor] = {}
-        for k, v in state_dict.items():
-            if not k.startswith(prefix) or not isinstance(v, Tensor):
-                continue
+        mine = [(k, v) for k, v in state_dict.items() if k.startswith(prefix) and isinstance(v, Tensor)]
+        unknown, bad = [], []
+        for k, v in mine:
             name = flat_param_name(k[len(prefix):])
             if name not in want:
-                unexpected.append(k)
+                unknown.append(k)
                 continue
             if tuple(v.shape) != want[name]:
-                errors.append(f"size mismatch for {k}: checkpoint {tuple(v.shape)} vs model {want[name]}")
+                bad.append(f"size mismatch for {k}: checkpoint {tuple(v.shape)} vs model {want[name]}")
                 continue
-            got[name] = v.detach().to(torch.float32).cpu().contiguous()
+            got[name] = v
+        if len(unknown) * 2 >= len(mine) and len(mine) > 0:
+            # names this package does not know (a checkpoint written by the upstream classes): map the
+            # tensors by registration order and shape (checkpoint.py); on failure the name-based report below stands
+            from .checkpoint import structural_key_map
+            try:
+                m = structural_key_map([(k, tuple(v.shape)) for k, v in mine], self.cfg, dict(mine))
+                got = {m[k]: v for k, v in mine if not m[k].endswith("#alias")}
+                unknown, bad = [], []
+                self.key_map = {k: m[k] for k, _ in mine}
+            except KeyError as e:
+                self.key_map_error = str(e)
+                if bad == [] and strict:
+                    errors.append(f"structural key mapping failed: {e}")
+        unexpected.extend(unknown)
+        errors.extend(bad)
+        got = {n: v.detach().to(torch.float32).cpu().contiguous() for n, v in got.items()}
+        n_missing = 0
         for name in want:
             if name not in got:
                 missing.append(prefix + name)
-        if not errors and (not missing or not strict):
+                n_missing += 1
+        if not errors and (n_missing == 0 or not strict):
             if self._net is not None and self._net._finalized:
                 self._net = None                       # re-load: a fresh engine is built from the new weights
             self._staged = got

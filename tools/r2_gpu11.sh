@@ -1,0 +1,10 @@
+#!/bin/bash
+# Round-2 GPU session 11: depth-1 resident-weight kernels at two CTAs per SM.
+mkdir -p gpurun_out
+O=gpurun_out/r2k
+( timeout 900 python -m pytest tests -q -x -m gpu ) > ${O}_pytest.out 2>&1
+echo "pytest rc=$?"; tail -3 ${O}_pytest.out
+python tools/op_profile.py > ${O}_op_profile.txt 2> ${O}_op_profile.err; echo "op_profile rc=$?"; head -1 ${O}_op_profile.txt
+grep "^rk\|^d0" ${O}_op_profile.txt
+( timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 ) > ${O}_bench.out 2> ${O}_bench.err
+echo "bench rc=$?"; grep '^{' ${O}_bench.out | cut -c1-200
