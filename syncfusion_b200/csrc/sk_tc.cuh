@@ -88,6 +88,7 @@ template <int BN> struct SkCfg {
 };
 // Ring depths per op class under the 227 KB budget (host side).  The mainloop of the k = 3 convs wants A stages (load ->
 // in-place transform -> MMA each hold one), the HBM-bound 1 x 1 ops want residual chunks in flight.
+template <int BN> inline bool fits_static(int a, int b2, int r, int epi12) { return SkCfg<BN>::smem_bytes(a, b2, r, epi12) <= SkCfg<BN>::kMaxSmem; }
 template <int BN>
 inline void sk_pick_rings(int taps, int xf, bool uses_r, bool has_resid, int epi12, int& na, int& nb, int& nr) {
   using C = SkCfg<BN>;
@@ -96,6 +97,11 @@ inline void sk_pick_rings(int taps, int xf, bool uses_r, bool has_resid, int epi
   else if (epi12) { na = uses_r ? 2 : 3; nr = uses_r ? 5 : 0; }
   else { na = 2; nr = uses_r ? 4 : 0; }
   if (uses_r && !has_resid) nr = npar;      // plain output staging: exactly one private slot per chunk group
+  if (const char* e = getenv(taps == 3 ? "SFB_SK_RINGS3" : (has_resid ? "SFB_SK_RINGS1R" : "SFB_SK_RINGS1"))) {   // tuning aid: "na,nb,nr"
+    int a = 0, b2 = 0, r = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b2, &r) == 3 && a >= 2 && b2 >= 2 && a <= C::MAX_NA && b2 <= C::MAX_NB && r <= C::MAX_NR &&
+        r >= (uses_r ? (has_resid ? 2 : npar) : 0) && fits_static<BN>(a, b2, uses_r ? r : 0, epi12)) { na = a; nb = b2; nr = uses_r ? r : 0; return; }
+  }
   const int nr_min = uses_r ? (has_resid ? 2 : npar) : 0;
   auto fits = [&](int a, int b2, int r) { return C::smem_bytes(a, b2, r, epi12) <= C::kMaxSmem; };
   nb = taps == 3 ? C::MAX_NB : na + 1;      // one weight tile per tap: a 1 x 1 op never runs further ahead on B than on A
