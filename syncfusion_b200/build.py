@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False, wait_log: "int | None" = N
         return LIB
     level = wait_log if wait_log is not None else (int(os.environ["SFB_WAIT_LOG"]) if os.environ.get("SFB_WAIT_LOG") else None)
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
-           "-DSFB_NO_FAST_MATH", *(["-DSFB_RK_PIPE"] if os.environ.get("SFB_RK_PIPE") else []),
+           "-DSFB_NO_FAST_MATH", *(["-DSFB_RK_PIPE"] if os.environ.get("SFB_RK_PIPE") else []), *(["-DSFB_ATTN_TL"] if os.environ.get("SFB_ATTN_TL") else []),
            *([f"-DSFB_WAIT_LOG={level}"] if level is not None else []), "-Xcompiler", "-fPIC", "-shared",
            "-Xptxas", "-v" if verbose else "-O3", "-o", str(target)] + [str(CSRC / s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -31,7 +31,13 @@ struct AttnParams {
                                 // cross: q in a [.., 512] tensor, k | v in a [.., 1024] tensor)
   float scale_log2;   // log2(e) / sqrt(64)
   int tag;            // plan op index (wait log)
+  long long* dbg;     // optional timeline (CTA 0 only): [role][tile][8] clock64 stamps (tools/attn_timeline.py)
 };
+#ifdef SFB_ATTN_TL      // build with -DSFB_ATTN_TL (python -m syncfusion_b200.build with SFB_ATTN_TL=1) for the per-warp timeline
+#define ATTN_STAMP(role, j, k) do { if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 32) p.dbg[((role) * 32 + (j)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define ATTN_STAMP(role, j, k) do { } while (0)
+#endif
 
 template <typename T> struct AttnCfg;
 template <> struct AttnCfg<__nv_bfloat16> { static constexpr int BKV = 128; };
@@ -170,7 +176,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
         issue_s(s2);
         umma_commit(s_full);
       }
+      ATTN_STAMP(4, j, 0);
       mbar_wait(p_ready, j & 1);
+      ATTN_STAMP(4, j, 1);
       tc_fence_after();
       issue_o(s, j > 0);
       umma_commit(o_full);
@@ -186,12 +194,15 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
     const float sc = p.scale_log2;
     for (int j = 0; j < nkv; ++j) {
       const int kv_valid = min(BKV, p.kv_tokens - j * BKV);
+      if (lane == 0) ATTN_STAMP(warp - 2, j, 0);
       mbar_wait(s_full, j & 1);
+      if (lane == 0) ATTN_STAMP(warp - 2, j, 1);
       tc_fence_after();
       uint32_t v[BKV];
 #pragma unroll
       for (int c = 0; c < BKV; c += 32) tmem_ld32(tmem_S + lane_off + c, v + c);
       tmem_ld_wait();
+      if (lane == 0) ATTN_STAMP(warp - 2, j, 2);
       tc_fence_before();
       mbar_arrive(s_free);                       // the S columns may be overwritten by S(j+1)
       if (kv_valid != BKV) {                     // tile-uniform: only the last tile of a ragged sequence is masked
@@ -233,6 +244,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
           tmem_st_wait();
         }
       }
+      if (lane == 0) ATTN_STAMP(warp - 2, j, 3);
       const float moff = m_used * sc;
       float rs0 = 0.f, rs1 = 0.f;
       // probabilities in place (fp32), row sum on the un-rounded values (two independent chains); the operand-precision
@@ -249,7 +261,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
         }
       }
       l_run += rs0 + rs1;
-      if (j > 0 && !o_waited) mbar_wait(o_full, (j - 1) & 1);   // P V(j-1) no longer reads the P columns
+      if (lane == 0) ATTN_STAMP(warp - 2, j, 4);
+      if (j > 0 && !o_waited) mbar_wait(o_full, (j - 1) & 1);
+      if (lane == 0) ATTN_STAMP(warp - 2, j, 5);   // P V(j-1) no longer reads the P columns
       // this row's probabilities (operand precision) into the P columns of tensor memory: no shared-memory tile, no
       // generic -> async proxy fence; the P V MMA takes its A operand straight from TMEM
 #pragma unroll
@@ -257,6 +271,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready);
+      if (lane == 0) ATTN_STAMP(warp - 2, j, 6);
     }
     // O is complete in TMEM: normalise and store
     mbar_wait(o_full, (nkv - 1) & 1);

@@ -1948,7 +1948,30 @@ static int dbg_attn_t(const void* qkv, void* out, int B, int N, cudaStream_t st)
                      sizeof(T) == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
     return SFB_ERR_CUDA;
   p.out = reinterpret_cast<T*>(out); p.n_tokens = N; p.kv_tokens = N; p.q_col0 = 0; p.k_col0 = 512; p.v_col0 = 1024; p.scale_log2 = 1.4426950408889634f / 8.0f;
+  long long* tl = nullptr;
+  constexpr int kTl = 5 * 32 * 8;
+  if (getenv("SFB_ATTN_TIMELINE")) {      // device-clock stamps of CTA 0's softmax warps and MMA thread (tools/attn_timeline.py)
+    if (cudaMalloc(&tl, kTl * sizeof(long long)) != cudaSuccess) return SFB_ERR_CUDA;
+    cudaMemset(tl, 0, kTl * sizeof(long long));
+    p.dbg = tl;
+  }
   attn_tc_kernel<T><<<dim3((N + 127) / 128, 8, B), kAttnThreads, attn_smem_bytes<T>(), st>>>(p);
+  if (tl) {
+    std::vector<long long> h(kTl);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), tl, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(tl);
+    const long long t0 = h[0];
+    static const char* const nm[] = {"wait_s", "s_ready", "ld_done", "max_done", "exp_done", "o_ready", "p_arrived"};
+    for (int j = 0; j < 32 && h[j * 8] != 0; ++j) {
+      for (int w = 0; w < 4; ++w) {
+        fprintf(stderr, "tile %2d warp %d:", j, w + 2);
+        for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %6lld", nm[k], h[(w * 32 + j) * 8 + k] - t0);
+        fprintf(stderr, "\n");
+      }
+      fprintf(stderr, "tile %2d mma   : wait_p %6lld p_ready %6lld\n", j, h[(4 * 32 + j) * 8] - t0, h[(4 * 32 + j) * 8 + 1] - t0);
+    }
+  }
   return cudaGetLastError() == cudaSuccess ? SFB_OK : SFB_ERR_CUDA;
 }
 extern "C" {
