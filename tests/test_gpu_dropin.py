@@ -14,7 +14,7 @@ import torch
 
 from oracle import Encoder1d as OracleEncoder
 from oracle.postprocess import postprocess as oracle_postprocess
-from tests.util import SMALL, make_encoder, make_oracle, rel_l2
+from tests.util import SMALL, make_encoder, make_inputs, make_oracle, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -112,3 +112,33 @@ def test_generation_sequence_on_gpu_matches_oracle(cuda_device, precision):
     torch.cuda.synchronize()
     assert tuple(out.shape) == tuple(out_ref.shape) == (B, 1, int(np.ceil(cut * 147 / 320)))
     assert rel_l2(out.cpu(), out_ref) < (2e-3 if precision == "fp32" else 5e-2)
+
+
+def test_foreign_checkpoint_names_sample_identically(cuda_device):
+    """f-3: the same weights under opaque closure-Module style names, another group order and an aliased time MLP load
+    through the parent's strict ``load_state_dict`` (structural key mapping) and sample bit-identically."""
+    import syncfusion_b200 as sf
+    from syncfusion_b200.checkpoint import canonical_entries
+    from syncfusion_b200.model import flat_param_name
+    cfg = sf.UNetConfig(precision="bf16", **SMALL)
+    om = make_oracle(SMALL, stress=True)
+    flat = {flat_param_name(k): v for k, v in om.net.state_dict().items()}
+    foreign = {}
+    for n, (name, shape, alias) in enumerate(canonical_entries(cfg, ("skip", "down", "items_down", "inner", "items_up", "up"), ("time", "fixed", "unet"))):
+        foreign[f"model.net.blocks.{n // 5}.blocks.{n % 5}.p"] = flat[alias or name]
+
+    class Parent(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = sf.DiffusionModel(cfg)
+
+    a, b = Parent(), Parent()
+    res = a.load_state_dict(foreign)
+    assert not res.missing_keys and not res.unexpected_keys
+    b.load_state_dict({"model.net." + k: v for k, v in om.net.state_dict().items()})
+    a.to(cuda_device); b.to(cuda_device)
+    x, ch, e = make_inputs(om.net.cfg, 2, 2048)
+    kw = dict(num_steps=3, channels=[c.to(cuda_device) for c in ch], embedding=e.to(cuda_device), embedding_scale=2.0)
+    out_a = a.model.sample(x_noisy=x.to(cuda_device), **kw)
+    out_b = b.model.sample(x_noisy=x.to(cuda_device), **kw)
+    assert torch.equal(out_a, out_b)
