@@ -40,7 +40,7 @@ struct AttnParams {
 #endif
 
 template <typename T> struct AttnCfg;
-template <> struct AttnCfg<__nv_bfloat16> { static constexpr int BKV = 128; };
+template <> struct AttnCfg<__nv_bfloat16> { static constexpr int BKV = 64; };      // attn2_tc_kernel below
 template <> struct AttnCfg<float> { static constexpr int BKV = 64; };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {   // FMNMX3
@@ -309,6 +309,232 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attn_tc_kernel(const __grid_c
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+
+// ------------------------------------------------------------------------------------------------ attention, second form
+// bf16 only (fp32 / TF32 mode keeps attn_tc_kernel above).  Same math as attn_tc_kernel, re-shaped for MORE RESIDENT WARPS per scheduler: the first form keeps a whole
+// 128-key score row in registers (168 registers, two CTAs per SM, two softmax warps per scheduler running a serial
+// TMEM-load -> max -> exp2 -> store chain at 61 % of the MUFU floor).  Here a key tile is 64 wide, the row is taken from
+// tensor memory in 32-column chunks TWICE (pass 1: row max; pass 2: exp2, row sum, P) so a thread never holds more than
+// one chunk, and P overwrites the S columns it came from (chunk c of P = 16 packed columns lands in S columns the same
+// thread has already consumed).  TMEM per CTA: S | P 64 + O 64 = 128 columns; shared memory 48 KB; ~80 registers:
+// FOUR CTAs per SM.  A CTA is strictly serial (S(j) -> softmax(j) -> P V(j) -> S(j+1)); the overlap comes from the
+// other three CTAs on the SM.  With four softmax warps per scheduler the kernel is issue bound, not MUFU bound: computing
+// a quarter / third / half of the exponentials with a cubic on the FMA pipe made it 5 / 10 / 16 % SLOWER (measured).
+constexpr int kAttn2Threads = 192;
+constexpr int kAttn2Stages = 2;       // two K/V stages: 48 KB per CTA (three stages at three CTAs per SM measured 13 % slower)
+constexpr int kAttn2BKV = 64;
+__host__ __device__ constexpr int attn2_smem_bytes() { return 128 * 128 /*Q*/ + kAttn2Stages * 2 * kAttn2BKV * 128 /*K, V*/ + 256; }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kAttn2Threads, 4) attn2_tc_kernel(const __grid_constant__ AttnParams<__nv_bfloat16> p) {
+  pdl_trigger();
+  constexpr int BKV = kAttn2BKV, NS = kAttn2Stages;
+  constexpr int kQBytes = 128 * 128, kKBytes = BKV * 128;
+  constexpr uint32_t kTmemCols = 128;           // S | P: [0, 64), O: [64, 128)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + kQBytes;                  // stage s: K at sKV + s*2*kKBytes, V right after K
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + NS * 2 * kKBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;    // [NS <= 4]
+  uint64_t* kv_empty = bars + 5;   // [NS]
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_ready = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (p.kv_tokens + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  pdl_wait();
+  mark_progress(p.tag);
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + BKV;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------- TMA producer
+    mbar_expect_tx(q_full, kQBytes);
+    tma_load_3d(sQ, &p.tmQ, q_full, p.q_col0 + h * kHeadDim, q0, b);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      mbar_expect_tx(&kv_full[s], 2 * kKBytes);
+      uint8_t* sk = sKV + s * 2 * kKBytes;
+      tma_load_3d(sk, &p.tmKV, &kv_full[s], p.k_col0 + h * kHeadDim, j * BKV, b);
+      tma_load_3d(sk + kKBytes, &p.tmV, &kv_full[s], p.v_col0 + h * kHeadDim, j * BKV, b);
+      if (++s == NS) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------- MMA issuer (the tensor pipe runs a CTA's MMAs in issue order)
+    constexpr uint32_t idesc_s = make_idesc(1, 128, BKV, 0, 0);        // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_o = make_idesc(1, 128, kHeadDim, 0, 1);   // P (TMEM) x V (MN-major)
+    mbar_wait(q_full, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&kv_full[s], ph);
+      tc_fence_after();
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sKV + s * 2 * kKBytes), av = ak + kKBytes;
+#pragma unroll
+      for (int k = 0; k < kHeadDim / 16; ++k)       // S(j) = Q K(j)^T: overwrites P(j-1), which P V(j-1) (issued before) has consumed
+        umma_ss<false>(tmem_S, make_smem_desc_sw128(aq + k * 32, 16, 1024), make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc_s, k != 0);
+      umma_commit(s_full);
+      mbar_wait(p_ready, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k)            // O (+)= P V: P from tensor memory (8 columns per k step), V MN-major from its TMA tile
+        umma_ts<false>(tmem_O, tmem_S + k * 8, make_smem_desc(av + k * 16 * 128, BKV * 128, 1024, 2), idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+      umma_commit(&kv_empty[s]);
+      if (j + 1 == nkv) umma_commit(o_full);
+      if (++s == NS) { s = 0; ph ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------- softmax (one query row per thread, 32-column chunks)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+    float m_used = -INFINITY, l_run = 0.f;
+    const float sc = p.scale_log2;
+    for (int j = 0; j < nkv; ++j) {
+      const int kv_valid = min(BKV, p.kv_tokens - j * BKV);
+      mbar_wait(s_full, j & 1);                  // S(j) complete - and with it P V(j-1): O may be rescaled, P may be overwritten
+      tc_fence_after();
+      // pass 1: row max
+      float mx;
+      {
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < BKV; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c, v);
+          tmem_ld_wait();
+          if (kv_valid != BKV) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i >= kv_valid) v[i] = 0xFF800000u;   // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            mx0 = fmax3(mx0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            mx1 = fmax3(mx1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            mx2 = fmax3(mx2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+            mx3 = fmax3(mx3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
+          }
+        }
+        mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      }
+      // lazy running max: rescale only when this row's max grew by more than 2^8 relative to the max in use
+      const bool need = (mx - m_used) * sc > 8.f;             // true on the first tile (m_used = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ((m_used == -INFINITY) ? 0.f : exp2f((m_used - mx) * sc)) : 1.f;
+        if (need) m_used = mx;
+        l_run *= alpha;
+        if (j > 0) {               // O(j-1) is complete (s_full): read - scale - write back (whole warp, per-lane factor)
+#pragma unroll
+          for (int c = 0; c < kHeadDim; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_off + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: probabilities, row sum (un-rounded values), P in operand precision over the consumed S columns
+      const float moff = m_used * sc;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c, v);
+        tmem_ld_wait();
+        if (kv_valid != BKV) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i >= kv_valid) v[i] = 0xFF800000u;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, -moff)), p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, -moff));
+          rs0 += p0; rs1 += p1;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        tmem_st16(tmem_S + lane_off + (c >> 1), pk);          // P columns [c / 2, c / 2 + 16): S columns this thread has already read
+      }
+      l_run += rs0 + rs1;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // O is complete in TMEM: normalise and store
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / l_run;
+    const bool valid = q0 + r < p.n_tokens;
+    __nv_bfloat16* dst = p.out + ((size_t)b * p.n_tokens + q0 + r) * 512 + h * kHeadDim;
+#pragma unroll
+    for (int c = 0; c < kHeadDim; c += 32) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_off + c, o);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(o[c8 + 2 * t]) * inv, __uint_as_float(o[c8 + 2 * t + 1]) * inv);
+            w[t] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          *reinterpret_cast<uint4*>(dst + c + c8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// launch of the attention core of one plan op / debug call (bf16: the second form when it is compiled in)
+template <typename T>
+inline cudaError_t attn_set_attrs() {
+  if constexpr (sizeof(T) == 2) return cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn2_smem_bytes());
+  else return cudaFuncSetAttribute(attn_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<T>());
+}
+template <typename T>
+inline void attn_launch(dim3 grid, cudaStream_t st, const AttnParams<T>& p) {
+  if constexpr (sizeof(T) == 2) launch_pdl(attn2_tc_kernel, grid, kAttn2Threads, attn2_smem_bytes(), st, p);
+  else launch_pdl(attn_tc_kernel<T>, grid, kAttnThreads, attn_smem_bytes<T>(), st, p);
 }
 
 }  // namespace sfb

@@ -273,7 +273,7 @@ cudaError_t set_kernel_attrs() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(gemm_tc_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<T, 256>());
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attn_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<T>());
+  e = attn_set_attrs<T>();
   return e;
 }
 int pick_bn(int N) {
@@ -1395,7 +1395,7 @@ struct Engine : EngineBase {
     } else if (o.kind == OP_ATTN) {
       static const char* const names[] = {"q_full", "kv_full", "kv_empty", "s_full", "p_ready", "o_full", "s_free"};
       static const int counts[] = {1, 4, 4, 1, 1, 1, 1};
-      name_of((uint32_t)attn_smem_bytes<T>() - 256, names, counts, 7);
+      name_of((uint32_t)(sizeof(T) == 2 ? attn2_smem_bytes() : attn_smem_bytes<T>()) - 256, names, counts, 7);   // both forms lay their barriers out alike
     }
     return out;
   }
@@ -1435,12 +1435,13 @@ struct Engine : EngineBase {
       }
     }
     if (!fold_items.empty()) {
-      if (fold_items.size() > fold_items_cap) {
-        void* d = nullptr;
-        if (cudaMalloc(&d, fold_items.size() * sizeof(FoldItem)) != cudaSuccess) { plan.ops.clear(); return fail(SFB_ERR_CUDA, "fold table alloc"); }
-        owned.push_back(d);
-        fold_items_dev = reinterpret_cast<FoldItem*>(d); fold_items_cap = fold_items.size();
-      }
+      // A FRESH device table per plan: kernels of the previous plan, enqueued asynchronously on the caller's stream by an
+      // earlier sample(), may still be reading the old one (a blocking copy on the legacy stream does not order against a
+      // non-blocking stream).  Plans are rebuilt only when (B, L, CFG, M, workspace) change; the tables are a few KB.
+      void* d = nullptr;
+      if (cudaMalloc(&d, fold_items.size() * sizeof(FoldItem)) != cudaSuccess) { plan.ops.clear(); return fail(SFB_ERR_CUDA, "fold table alloc"); }
+      owned.push_back(d);
+      fold_items_dev = reinterpret_cast<FoldItem*>(d); fold_items_cap = fold_items.size();
       if (cudaMemcpy(fold_items_dev, fold_items.data(), fold_items.size() * sizeof(FoldItem), cudaMemcpyHostToDevice) != cudaSuccess) {
         plan.ops.clear();
         return fail(SFB_ERR_CUDA, "fold table upload");
@@ -1589,7 +1590,7 @@ struct Engine : EngineBase {
           break;
         case OP_ATTN: {
           dim3 grid((o.L + 127) / 128, 8, o.B);
-          launch_pdl(attn_tc_kernel<T>, grid, kAttnThreads, attn_smem_bytes<T>(), st, o.ap);
+          attn_launch<T>(grid, st, o.ap);
           break;
         }
       }
@@ -1955,7 +1956,7 @@ static int dbg_attn_t(const void* qkv, void* out, int B, int N, cudaStream_t st)
     cudaMemset(tl, 0, kTl * sizeof(long long));
     p.dbg = tl;
   }
-  attn_tc_kernel<T><<<dim3((N + 127) / 128, 8, B), kAttnThreads, attn_smem_bytes<T>(), st>>>(p);
+  attn_launch<T>(dim3((N + 127) / 128, 8, B), st, p);
   if (tl) {
     std::vector<long long> h(kTl);
     cudaStreamSynchronize(st);
