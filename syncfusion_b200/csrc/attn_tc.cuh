@@ -2,13 +2,18 @@
 //   out[b, i, h, :] = softmax_j(q[b,i,h,:] . k[b,j,h,:] / sqrt(64)) v[b,j,h,:]     8 heads x 64, non-causal, no mask.
 // Input is the fused QKV projection output [B, N, 1536] (q | k | v, heads contiguous 64-wide), output [B, N, 512].
 //
+// Two forms: attn_tc_kernel<T> (this one; 128-key tiles in bf16 / 64 in TF32, the whole score row in registers, two CTAs
+// per SM - used by fp32 mode) and attn2_tc_kernel (bf16, further down: 64-key tiles, chunked two-pass softmax, four CTAs
+// per SM - the bf16 path).
+//
 // One CTA = one 128-query tile of one (clip, head), two CTAs per SM.  Warp 0 lane 0: TMA producer (Q once, K/V tiles
 // in a three-stage ring).  Warp 1 lane 0: tcgen05.mma issuer: S = Q K^T (K-major x K-major) into TMEM, O += P V
 // ACCUMULATED IN TMEM over all key tiles (P is the A operand read FROM TENSOR MEMORY, V is consumed straight from its
 // TMA tile as an MN-major B operand).  Warps 2-5 (128 threads, one query row each): S is read from TMEM ONCE into
 // registers (which frees the S columns at once: the MMA warp issues S(j+1) while softmax(j) is still computing), row
 // max (FMNMX3), exp2, P written back to its own TMEM columns in operand precision with tcgen05.st - no shared-memory P
-// tile, no generic -> async proxy fence on the softmax -> MMA hand-off.  The running max is LAZY: the O accumulator and the row sum are rescaled only when a row's max grows by
+// tile, no generic -> async proxy fence on the softmax -> MMA hand-off.  The running max is LAZY: the O accumulator and
+// the row sum are rescaled only when a row's max grows by
 // more than 2^8 (then the warp reads O from TMEM, scales, writes it back); otherwise probabilities simply stay
 // relative to the older max (<= 2^8, exact in fp32 / harmless in bf16) - no per-tile O read-back, no per-tile
 // multiply of the accumulator.  The [B, 8, N, N] score matrix the reference materialises never exists.
