@@ -1543,7 +1543,7 @@ struct Engine : EngineBase {
                      o.stats_out, o.L, 1e-5f);
           break;
         case OP_D0_UP:
-          launch_pdl(d0_up_kernel<T>, dim3(lb, o.B), 256, 0, st, reinterpret_cast<const T*>(o.in), o.w0, o.fscalar, sc.frow + o.ft_off,
+          launch_pdl(d0_up_kernel<T>, dim3((unsigned)((o.L + 1023) / 1024), o.B), 256, 0, st, reinterpret_cast<const T*>(o.in), o.w0, o.fscalar, sc.frow + o.ft_off,
                                                         sc.bstride, sc.bmod, sc.x, o.out_r, o.L, Bx, o.taps);
           break;
         case OP_GEMM: {
