@@ -1708,7 +1708,11 @@ struct Engine : EngineBase {
     }
     const size_t n = (size_t)B * L;
     float* xs = at<float>(plan.lay.xstate);
-    const bool graphable = use_graph && !profiling && !traj_x && !traj_v && !teacher_x;
+    bool graphable = use_graph && !profiling && !traj_x && !traj_v && !teacher_x;
+    if (graphable) {       // a caller that is itself capturing `st` gets the plain launches recorded into ITS graph
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); graphable = false; }
+    }
     // Whole-loop CUDA graph (SFB_GRAPH=0 turns it off): the per-call preparation (tables, cross-attention
     // biases, onset pyramid: the only kernels that read the caller's buffers) runs eagerly, the num_steps x 169 launches
     // of the sampling loop - which touch the workspace only - are captured once per (plan, steps, scale), programmatic-

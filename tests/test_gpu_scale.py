@@ -182,3 +182,28 @@ def test_wait_timeout_is_reported_and_named(dev):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fault_inject.py")], capture_output=True, text=True, timeout=180)
     assert "FAULT_INJECT_OK" in r.stdout, r.stdout + r.stderr
     assert "barrier wait timed out" in r.stdout and "sfb.cu:" in r.stdout
+
+
+def test_cuda_graph_replay_matches_eager(dev, monkeypatch):
+    """the captured sampling loop (default) and the eager launches (SFB_GRAPH=0) give bit-identical waveforms,
+    on the capture call, on replays with OTHER input buffers (the graph touches the workspace only), for a second step
+    count (second cached graph) and after a plan change."""
+    import syncfusion_b200 as sf
+    from tests.util import SMALL
+    om = make_oracle(SMALL, stress=True)
+    sd = om.net.state_dict()
+
+    def build(flag):
+        monkeypatch.setenv("SFB_GRAPH", flag)
+        m = sf.DiffusionModel(sf.UNetConfig(precision="bf16", **SMALL), dev)
+        m.load_state_dict(sd)
+        return m
+
+    eager, graph = build("0"), build("1")
+    for (B, L, steps, scale, seed) in [(2, 2048, 4, 2.0, 1), (2, 2048, 4, 2.0, 2), (2, 2048, 6, 2.0, 3), (3, 1024, 4, 1.0, 4), (2, 2048, 4, 2.0, 5)]:
+        x, ch, e = _inputs(om, B, L, dev, seed=seed)
+        kw = dict(num_steps=steps, channels=ch, embedding=e, embedding_scale=scale)
+        a = eager.sample(x_noisy=x, **kw)
+        b = graph.sample(x_noisy=x.clone(), **kw)
+        assert torch.equal(a, b), (B, L, steps, scale, seed)
+    assert graph.net.last_launch_count == eager.net.last_launch_count
