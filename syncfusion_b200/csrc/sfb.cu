@@ -1715,8 +1715,8 @@ struct Engine : EngineBase {
     }
     // Whole-loop CUDA graph (SFB_GRAPH=0 turns it off): the per-call preparation (tables, cross-attention
     // biases, onset pyramid: the only kernels that read the caller's buffers) runs eagerly, the num_steps x 169 launches
-    // of the sampling loop - which touch the workspace only - are captured once per (plan, steps, scale), programmatic-
-    // dependent-launch edges included, and replayed with ONE launch: +4 % at the bench shape (the stream's front end no
+    // of the sampling loop - which touch the workspace only - are captured once per (plan, steps, scale) as plain kernel
+    // nodes and replayed with ONE launch: +4 % at the bench shape (the stream's front end no
     // longer meters 8.5 k launches).  Capture and replay run on an internal stream (the caller's may be the legacy default
     // stream, which cannot be captured); events order it after the caller's earlier work and the caller's later work after it.
     cudaStream_t ws_st = st;
@@ -1763,7 +1763,9 @@ struct Engine : EngineBase {
       if (!hit) {
         const int64_t before = launches;
         SFB_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        g_pdl_suppress = getenv("SFB_GRAPH_PDL") == nullptr;      // plain kernel nodes (ptx.cuh); SFB_GRAPH_PDL=1 keeps the programmatic edges
         rc = loop(gs);
+        g_pdl_suppress = false;
         cudaGraph_t graph = nullptr;
         const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
