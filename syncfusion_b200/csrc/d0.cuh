@@ -381,6 +381,343 @@ __global__ void __launch_bounds__(256, 3) d0_gn_conv1_kernel(const float* __rest
   if (stats_out) d0_flush_stats(sm, fa, fq, stats_out + (size_t)b * 16);
 }
 
+// ---------------------------------------------------------------------------------------------------- depth-0 conv on tcgen05
+// bf16 mode.  The k = 3, 8 -> 8 channel conv is 192 of the ~500 CUDA-core instructions d0_gn_conv1 spends per position
+// (ncu: 56 % issue-slot utilisation at 1.8 TB/s - the kernel is bound by its instruction stream, not by HBM).  Here it
+// runs on the tensor core with NO im2col: the activated tile is stored channels-last in shared memory, 16 bytes (8 bf16
+// channels) per position, and that dense array IS the K-major, un-swizzled A operand of a K = 16 MMA whose descriptor
+// says "the next 16 bytes of K are 16 bytes further on" (LBO = 16 B) - i.e. K chunk 0 of row r is position r, K chunk 1 is
+// position r + 1: overlapping rows.  Two MMAs per 128 positions (taps -1 | 0, then +1 | a zero-weight chunk), N = 16
+// (8 output channels + 8 zero columns), fp32 accumulators in TMEM, one thread per position in the epilogue.
+constexpr int kD0TcTile = 1024;                       // positions per CTA (eight 128-row MMA blocks)
+constexpr int kD0TcRows = kD0TcTile + 3;              // rows -1 .. 1025 of the tile: halo + the zero-weight chunk's last row
+struct alignas(128) D0TcSmem {
+  uint8_t a[(kD0TcRows + 5) * 16];                    // activated bf16 rows, 16 B each (core matrix = 8 consecutive rows)
+  uint8_t b[2][512];                                  // per MMA: [k_blk][n_blk] core matrices of 8 (n) x 16 B
+  float ab[16];
+  double red[16];
+  uint64_t bar;
+  uint32_t tslot;
+};
+__device__ __forceinline__ uint32_t d0_pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// SiLU(2 h) = h + h tanh(h) with ONE MUFU op (tanh.approx.f32: relative error 2^-11, below the bf16 rounding of the result);
+// the caller folds the 1/2 into the GroupNorm coefficients.
+__device__ __forceinline__ float silu_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+// Sum 16 per-lane doubles over the warp with 16 shuffles instead of 80: at every step a lane keeps half of its values and
+// hands the other half to its partner.  Afterwards lane l holds the total of value index
+// ((l >> 4) & 1) * 8 + ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1)   (lanes l and l ^ 1 hold the same total).
+__device__ __forceinline__ double warp_reduce16(const double (&v)[16], int lane) {
+  double w8[8], w4[4], w2[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const double keep = h16 ? v[8 + i] : v[i], send = h16 ? v[i] : v[8 + i]; w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const double keep = h8 ? w8[4 + i] : w8[i], send = h8 ? w8[i] : w8[4 + i]; w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { const double keep = h4 ? w4[2 + i] : w4[i], send = h4 ? w4[i] : w4[2 + i]; w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+  const double keep = h2 ? w2[1] : w2[0], send = h2 ? w2[0] : w2[1];
+  double r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// y[0..8) += x * w[0..8)   (w: 8 consecutive floats in shared memory, 16-byte aligned; fma.rn.f32x2)
+__device__ __forceinline__ void axpy8(unsigned long long (&y)[4], float x, const float* w) {
+  const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(w), w1 = *reinterpret_cast<const ulonglong2*>(w + 4);
+  const unsigned long long xx = f2pack(x, x);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(y[0]) : "l"(xx), "l"(w0.x));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(y[1]) : "l"(xx), "l"(w0.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(y[2]) : "l"(xx), "l"(w1.x));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(y[3]) : "l"(xx), "l"(w1.y));
+}
+__device__ __forceinline__ void umma_ss_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// x [B, L, 8] f32 -> h [B, L, 8] bf16 ; w [24][8] f32 (k = tap * 8 + ci, co fastest)
+__global__ void __launch_bounds__(256, 4) d0_gn_conv1_tc_kernel(const float* __restrict__ x, const double* __restrict__ stats_in,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const float* __restrict__ w, const float* __restrict__ bias,
+                                                                __nv_bfloat16* __restrict__ out_t, double* __restrict__ stats_out, int L, float eps) {
+  pdl_trigger();
+  __shared__ D0TcSmem sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = blockIdx.y;
+  const int base = blockIdx.x * kD0TcTile;
+  if (tid == 0) { mbar_init(&sm.bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&sm.tslot, 128); tmem_relinquish(); }
+  // weights -> the two B operands: B_m[n][k], n = output channel (8..15: zero), k = k_blk * 8 + ci, tap = 2 m + k_blk (tap 3: zero)
+  for (int i = tid; i < 2 * 16 * 16; i += 256) {
+    const int m = i >> 8, n = (i >> 4) & 15, k = i & 15;
+    const int k_blk = k >> 3, ci = k & 7, tap = 2 * m + k_blk;
+    const float v = (n < 8 && tap < 3) ? __ldg(&w[(tap * 8 + ci) * 8 + n]) : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(&sm.b[m][(k_blk * 2 + (n >> 3)) * 128 + (n & 7) * 16 + ci * 2]) = __float2bfloat16_rn(v);
+  }
+  float bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bs[j] = __ldg(&bias[j]);
+  tc_fence_before();
+  __syncthreads();
+  pdl_wait();
+  if (tid < 8) {      // per-channel GroupNorm coefficients (depth 0: 8 groups over 8 channels)
+    const double cnt = (double)L;
+    const double mean = stats_in[(size_t)b * 16 + tid * 2] / cnt;
+    double var = stats_in[(size_t)b * 16 + tid * 2 + 1] / cnt - mean * mean;
+    var = var > 0 ? var : 0;
+    const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[tid];
+    sm.ab[tid] = 0.5f * a;                                    // h = (GroupNorm(x)) / 2 for silu_half
+    sm.ab[8 + tid] = 0.5f * (beta[tid] - (float)mean * a);
+  }
+  if (tid < 16) sm.red[tid] = 0.0;
+  __syncthreads();
+  const float* xb = x + (size_t)b * L * 8;
+  // phase 1: GroupNorm + SiLU -> bf16 rows (row r = position base - 1 + r); rows outside the clip are the conv's zero padding
+  RawVec8<float> raw[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int r = tid + 256 * k, l = base - 1 + r;
+    if (r < kD0TcRows && l >= 0 && l < L) raw[k].load(xb + (size_t)l * 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int r = tid + 256 * k, l = base - 1 + r;
+    if (r < kD0TcRows + 5) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (r < kD0TcRows && l >= 0 && l < L) {
+        float xv[8], t[8];
+        raw[k].get(xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = silu_half(fmaf(xv[j], sm.ab[j], sm.ab[8 + j]));
+        o = make_uint4(d0_pack_bf16(t[0], t[1]), d0_pack_bf16(t[2], t[3]), d0_pack_bf16(t[4], t[5]), d0_pack_bf16(t[6], t[7]));
+      }
+      *reinterpret_cast<uint4*>(&sm.a[r * 16]) = o;
+    }
+  }
+  fence_proxy_async();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tslot;
+  if (tid == 0) {
+    // phase 2: A: K-major, no swizzle, core matrix = 8 rows x 16 B contiguous; next K chunk = next position (+16 B, LBO),
+    // next 8 rows = +128 B (SBO).  B: LBO = 256 B between the two K chunks, SBO = 128 B between the two 8-column groups.
+    constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, 16, 0, 0);
+    const uint32_t a0 = smem_u32(sm.a), b0 = smem_u32(sm.b[0]), b1 = smem_u32(sm.b[1]);
+#pragma unroll
+    for (int mb = 0; mb < kD0TcTile / 128; ++mb) {
+      umma_ss_f16(tmem_base + mb * 16, make_smem_desc(a0 + (mb * 128) * 16, 16, 128, 0), make_smem_desc(b0, 256, 128, 0), idesc, 0u);
+      umma_ss_f16(tmem_base + mb * 16, make_smem_desc(a0 + (mb * 128 + 2) * 16, 16, 128, 0), make_smem_desc(b1, 256, 128, 0), idesc, 1u);
+    }
+    umma_commit(&sm.bar);
+  }
+  while (!mbar_try_wait_hint(&sm.bar, 0)) {}
+  tc_fence_after();
+  // phase 3: one position per thread and MMA block: + bias -> bf16 h, GroupNorm sums of h
+  const int q = warp & 3, half = warp >> 2;
+  float fa[8], fq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { fa[j] = 0.f; fq[j] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mb = half * 4 + i;
+    uint32_t v[16];
+    tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + mb * 16, v);
+    tmem_ld_wait();
+    const int l = base + mb * 128 + q * 32 + lane;
+    if (l < L) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j] = __uint_as_float(v[j]) + bs[j]; fa[j] += o[j]; fq[j] = fmaf(o[j], o[j], fq[j]); }
+      Vec8<__nv_bfloat16>::store(out_t + ((size_t)b * L + l) * 8, o);
+    }
+  }
+  if (stats_out) {       // fp32 over the thread's four positions, fp64 from there on (16-shuffle warp reduction, one atomic per value)
+    double v16[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v16[j] = (double)fa[j]; v16[8 + j] = (double)fq[j]; }
+    const double tot = warp_reduce16(v16, lane);
+    if ((lane & 1) == 0) {
+      const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      atomicAdd(&sm.red[(idx & 7) * 2 + (idx >> 3)], tot);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (stats_out && tid < 16) atomicAdd(&stats_out[(size_t)b * 16 + tid], sm.red[tid]);
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// Second launch of the depth-0 item on the same scheme: y = Inject(Mod(LN(conv3(SiLU(GN2(h))) + b2 + x))) with the conv on
+// tcgen05 (h bf16 -> activated bf16 rows -> two overlapping-row MMAs per 128 positions) and the per-position tail
+// (residual, LayerNorm over the 8 channels, Modulation, InjectChannels 10 -> 8) in the one-position-per-thread epilogue.
+// The residual / context rows of a thread's four positions are requested BEFORE the accumulator wait.
+template <int CTX>
+__global__ void __launch_bounds__(256, 3) d0_tail_tc_kernel(const __nv_bfloat16* __restrict__ h, const double* __restrict__ stats_in,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            const float* x_r, const float* __restrict__ mod, int mod_bstride, int mod_bmod,
+                                                            const __nv_bfloat16* __restrict__ ctx, int Bc, const float* __restrict__ wi,
+                                                            const float* __restrict__ bi, const float* __restrict__ xbias, int xb_stride,
+                                                            float* out_r, __nv_bfloat16* __restrict__ out_t, double* __restrict__ stats_out, int L,
+                                                            float eps) {
+  pdl_trigger();
+  __shared__ D0TcSmem sm;
+  __shared__ __align__(16) float s_wi[(8 + CTX) * 8];
+  __shared__ float s_v[4 * 8];     // conv bias | 1 + mod scale | mod shift | inject bias + cross-attention bias
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = blockIdx.y;
+  const int base = blockIdx.x * kD0TcTile;
+  if (tid == 0) { mbar_init(&sm.bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&sm.tslot, 128); tmem_relinquish(); }
+  for (int i = tid; i < 2 * 16 * 16; i += 256) {
+    const int m = i >> 8, n = (i >> 4) & 15, k = i & 15;
+    const int k_blk = k >> 3, ci = k & 7, tap = 2 * m + k_blk;
+    const float v = (n < 8 && tap < 3) ? __ldg(&w[(tap * 8 + ci) * 8 + n]) : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(&sm.b[m][(k_blk * 2 + (n >> 3)) * 128 + (n & 7) * 16 + ci * 2]) = __float2bfloat16_rn(v);
+  }
+  for (int i = tid; i < (8 + CTX) * 8; i += 256) s_wi[i] = wi[i];
+  tc_fence_before();
+  __syncthreads();
+  pdl_wait();
+  if (tid < 8) {
+    const double cnt = (double)L;
+    const double mean = stats_in[(size_t)b * 16 + tid * 2] / cnt;
+    double var = stats_in[(size_t)b * 16 + tid * 2 + 1] / cnt - mean * mean;
+    var = var > 0 ? var : 0;
+    const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[tid];
+    sm.ab[tid] = 0.5f * a;
+    sm.ab[8 + tid] = 0.5f * (beta[tid] - (float)mean * a);
+    const float* md = mod + (size_t)(b % mod_bmod) * mod_bstride;
+    s_v[tid] = bias[tid];
+    s_v[8 + tid] = 1.f + md[tid];
+    s_v[16 + tid] = md[8 + tid];
+    s_v[24 + tid] = bi[tid] + (xbias ? xbias[(size_t)b * xb_stride + tid] : 0.f);
+  }
+  if (tid < 16) sm.red[tid] = 0.0;
+  __syncthreads();
+  const __nv_bfloat16* hb = h + (size_t)b * L * 8;
+  RawVec8<__nv_bfloat16> raw[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int r = tid + 256 * k, l = base - 1 + r;
+    if (r < kD0TcRows && l >= 0 && l < L) raw[k].load(hb + (size_t)l * 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int r = tid + 256 * k, l = base - 1 + r;
+    if (r < kD0TcRows + 5) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (r < kD0TcRows && l >= 0 && l < L) {
+        float xv[8], t[8];
+        raw[k].get(xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = silu_half(fmaf(xv[j], sm.ab[j], sm.ab[8 + j]));
+        o = make_uint4(d0_pack_bf16(t[0], t[1]), d0_pack_bf16(t[2], t[3]), d0_pack_bf16(t[4], t[5]), d0_pack_bf16(t[6], t[7]));
+      }
+      *reinterpret_cast<uint4*>(&sm.a[r * 16]) = o;
+    }
+  }
+  fence_proxy_async();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tslot;
+  if (tid == 0) {
+    constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, 16, 0, 0);
+    const uint32_t a0 = smem_u32(sm.a), b0 = smem_u32(sm.b[0]), b1 = smem_u32(sm.b[1]);
+#pragma unroll
+    for (int mb = 0; mb < kD0TcTile / 128; ++mb) {
+      umma_ss_f16(tmem_base + mb * 16, make_smem_desc(a0 + (mb * 128) * 16, 16, 128, 0), make_smem_desc(b0, 256, 128, 0), idesc, 0u);
+      umma_ss_f16(tmem_base + mb * 16, make_smem_desc(a0 + (mb * 128 + 2) * 16, 16, 128, 0), make_smem_desc(b1, 256, 128, 0), idesc, 1u);
+    }
+    umma_commit(&sm.bar);
+  }
+  // the residual and context rows of this thread's four positions, in flight while the MMAs run
+  const int q = warp & 3, half = warp >> 2;
+  const float* xr = x_r + (size_t)b * L * 8;
+  const __nv_bfloat16* cb = ctx + (size_t)(b % Bc) * L * CTX;
+  RawVec8<float> rr[4];
+  float rc[4][CTX];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int l = base + (half * 4 + i) * 128 + q * 32 + lane;
+    if (l < L) {
+      rr[i].load(xr + (size_t)l * 8);
+#pragma unroll
+      for (int ci = 0; ci < CTX; ++ci) rc[i][ci] = to_f32(cb[(size_t)l * CTX + ci]);
+    }
+  }
+  while (!mbar_try_wait_hint(&sm.bar, 0)) {}
+  tc_fence_after();
+  float fa[8], fq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { fa[j] = 0.f; fq[j] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mb = half * 4 + i;
+    uint32_t v[16];
+    tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + mb * 16, v);
+    tmem_ld_wait();
+    const int l = base + mb * 128 + q * 32 + lane;
+    if (l < L) {
+      float r8[8], acc[8];
+      rr[i].get(r8);
+      float mean = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[j] = __uint_as_float(v[j]) + s_v[j] + r8[j]; mean += acc[j]; }     // conv2 + b2 + x
+      mean *= 0.125f;
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = acc[j] - mean; var += d * d; }
+      const float rstd = rsqrtf(var * 0.125f + eps);
+      float m[8], y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { m[j] = (acc[j] - mean) * rstd * s_v[8 + j] + s_v[16 + j]; y[j] = m[j] + s_v[24 + j]; }
+      unsigned long long y2[4];          // the 10 -> 8 contraction as packed fp32 pairs (FFMA2: same rounding as two FFMAs)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y2[j] = f2pack(y[2 * j], y[2 * j + 1]);
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) axpy8(y2, m[ci], &s_wi[ci * 8]);
+#pragma unroll
+      for (int ci = 0; ci < CTX; ++ci) axpy8(y2, rc[i][ci], &s_wi[(8 + ci) * 8]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f2unpack(y2[j], y[2 * j], y[2 * j + 1]);
+      const size_t g = ((size_t)b * L + l) * 8;
+      Vec8<float>::store(out_r + g, y);
+      if (out_t) Vec8<__nv_bfloat16>::store(out_t + g, y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { fa[j] += y[j]; fq[j] = fmaf(y[j], y[j], fq[j]); }
+    }
+  }
+  if (stats_out) {
+    double v16[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v16[j] = (double)fa[j]; v16[8 + j] = (double)fq[j]; }
+    const double tot = warp_reduce16(v16, lane);
+    if ((lane & 1) == 0) {
+      const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      atomicAdd(&sm.red[(idx & 7) * 2 + (idx >> 3)], tot);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (stats_out && tid < 16) atomicAdd(&stats_out[(size_t)b * 16 + tid], sm.red[tid]);
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
 // h [B, L, 8] (T), x / out_r [B, L, 8] f32 (in place), ctx [Bc, L, CTX] (T), mod = scale[8] | shift[8] of clip b % mod_bmod,
 // wi [8 + CTX][8] f32 (k, co), xbias [B, xb_stride] or null.
 template <typename T, int CTX>

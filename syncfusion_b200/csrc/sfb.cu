@@ -318,6 +318,7 @@ struct Engine : EngineBase {
   bool no_rk = getenv("SFB_NO_RK") != nullptr;   // debugging aids: force the unfused generic path
   bool no_sk = getenv("SFB_NO_SK") != nullptr;
   bool no_d0_fused = getenv("SFB_NO_D0_FUSED") != nullptr;
+  bool d0_tc = !(getenv("SFB_D0_TC") != nullptr && atoi(getenv("SFB_D0_TC")) == 0);   // depth-0 convs on tcgen05 (d0.cuh, bf16 mode); SFB_D0_TC=0: CUDA-core form
 
   struct Op {
     int kind = 0, depth = 0, stack = 0, item = 0;
@@ -1533,10 +1534,26 @@ struct Engine : EngineBase {
                                                                reinterpret_cast<T*>(o.out_t), o.stats_out, o.L, Bx, XB_total);
           break;
         case OP_D0_CONV1:
+          if constexpr (sizeof(T) == 2) {
+            if (d0_tc) {
+              launch_pdl(d0_gn_conv1_tc_kernel, dim3((unsigned)((o.L + kD0TcTile - 1) / kD0TcTile), o.B), 256, 0, st, reinterpret_cast<const float*>(o.in),
+                         (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], reinterpret_cast<__nv_bfloat16*>(o.out_t), o.stats_out, o.L, 1e-5f);
+              break;
+            }
+          }
           launch_pdl(d0_gn_conv1_kernel<T>, dim3((unsigned)((o.L + d0_positions_per_block() - 1) / d0_positions_per_block()), o.B), 256, 0, st, reinterpret_cast<const float*>(o.in),
                      (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], reinterpret_cast<T*>(o.out_t), o.stats_out, o.L, 1e-5f);
           break;
         case OP_D0_TAIL:
+          if constexpr (sizeof(T) == 2) {
+            if (d0_tc) {
+              launch_pdl(d0_tail_tc_kernel<2>, dim3((unsigned)((o.L + kD0TcTile - 1) / kD0TcTile), o.B), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(o.in),
+                         (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], o.resid, sc.frow + o.ft_off, sc.bstride, sc.bmod,
+                         reinterpret_cast<const __nv_bfloat16*>(o.in2), Bx, o.wx[2], o.wx[3], o.w2, XB_total, o.out_r, reinterpret_cast<__nv_bfloat16*>(o.out_t),
+                         o.stats_out, o.L, 1e-5f);
+              break;
+            }
+          }
           launch_pdl(d0_tail_kernel<T, 2>, dim3((unsigned)((o.L + d0_positions_per_block() - 1) / d0_positions_per_block()), o.B), 256, 0, st, reinterpret_cast<const T*>(o.in),
                      (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], o.resid, sc.frow + o.ft_off, sc.bstride, sc.bmod,
                      reinterpret_cast<const T*>(o.in2), Bx, o.wx[2], o.wx[3], o.w2, XB_total, o.out_r, reinterpret_cast<T*>(o.out_t),
