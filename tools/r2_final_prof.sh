@@ -14,5 +14,6 @@ one() { # name kernel-regex skip
 one d6conv1 sk_kernel ${SK_SKIP:-153}
 one attn_d4 attn_tc_kernel 20
 one rk_d1inject rk_kernel 21
+one d0conv1_tc d0_gn_conv1_tc_kernel 2
 python tools/op_profile.py > ${O}_op_profile.txt 2>&1; head -1 ${O}_op_profile.txt
 ( timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 ) > ${O}_bench.out 2> ${O}_bench.err; echo "bench rc=$?"; grep '^{' ${O}_bench.out | cut -c1-300
