@@ -455,7 +455,7 @@ __device__ __forceinline__ void umma_ss_f16(uint32_t tmem_d, uint64_t desc_a, ui
 __global__ void __launch_bounds__(256, 4) d0_gn_conv1_tc_kernel(const float* __restrict__ x, const double* __restrict__ stats_in,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 const float* __restrict__ w, const float* __restrict__ bias,
-                                                                __nv_bfloat16* __restrict__ out_t, double* __restrict__ stats_out, int L, float eps) {
+                                                                __nv_bfloat16* __restrict__ out_t, double* __restrict__ stats_out, int L, float eps, int tag) {
   pdl_trigger();
   __shared__ D0TcSmem sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, b = blockIdx.y;
@@ -475,6 +475,7 @@ __global__ void __launch_bounds__(256, 4) d0_gn_conv1_tc_kernel(const float* __r
   tc_fence_before();
   __syncthreads();
   pdl_wait();
+  mark_progress(tag);
   if (tid < 8) {      // per-channel GroupNorm coefficients (depth 0: 8 groups over 8 channels)
     const double cnt = (double)L;
     const double mean = stats_in[(size_t)b * 16 + tid * 2] / cnt;
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(256, 4) d0_gn_conv1_tc_kernel(const float* __r
     }
     umma_commit(&sm.bar);
   }
-  while (!mbar_try_wait_hint(&sm.bar, 0)) {}
+  mbar_wait_at(&sm.bar, 0, (5u << 16) | __LINE__, (uint32_t)tag);      // bounded, logged wait (ptx.cuh; file id 5 = d0.cuh)
   tc_fence_after();
   // phase 3: one position per thread and MMA block: + bias -> bf16 h, GroupNorm sums of h
   const int q = warp & 3, half = warp >> 2;
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(256, 3) d0_tail_tc_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ ctx, int Bc, const float* __restrict__ wi,
                                                             const float* __restrict__ bi, const float* __restrict__ xbias, int xb_stride,
                                                             float* out_r, __nv_bfloat16* __restrict__ out_t, double* __restrict__ stats_out, int L,
-                                                            float eps) {
+                                                            float eps, int tag) {
   pdl_trigger();
   __shared__ D0TcSmem sm;
   __shared__ __align__(16) float s_wi[(8 + CTX) * 8];
@@ -593,6 +594,7 @@ __global__ void __launch_bounds__(256, 3) d0_tail_tc_kernel(const __nv_bfloat16*
   tc_fence_before();
   __syncthreads();
   pdl_wait();
+  mark_progress(tag);
   if (tid < 8) {
     const double cnt = (double)L;
     const double mean = stats_in[(size_t)b * 16 + tid * 2] / cnt;
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(256, 3) d0_tail_tc_kernel(const __nv_bfloat16*
       for (int ci = 0; ci < CTX; ++ci) rc[i][ci] = to_f32(cb[(size_t)l * CTX + ci]);
     }
   }
-  while (!mbar_try_wait_hint(&sm.bar, 0)) {}
+  mbar_wait_at(&sm.bar, 0, (5u << 16) | __LINE__, (uint32_t)tag);      // bounded, logged wait (ptx.cuh; file id 5 = d0.cuh)
   tc_fence_after();
   float fa[8], fq[8];
 #pragma unroll

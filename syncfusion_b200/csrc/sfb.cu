@@ -160,7 +160,7 @@ int wait_log_init() {
   return 0;
 }
 const char* wait_site_file(uint32_t id) {
-  switch (id) { case 9: return "sfb.cu"; case 1: return "gemm_tc.cuh"; case 2: return "attn_tc.cuh"; case 3: return "rk_tc.cuh"; case 4: return "sk_tc.cuh"; }
+  switch (id) { case 9: return "sfb.cu"; case 1: return "gemm_tc.cuh"; case 2: return "attn_tc.cuh"; case 3: return "rk_tc.cuh"; case 4: return "sk_tc.cuh"; case 5: return "d0.cuh"; }
   return "?";
 }
 
@@ -1537,7 +1537,7 @@ struct Engine : EngineBase {
           if constexpr (sizeof(T) == 2) {
             if (d0_tc) {
               launch_pdl(d0_gn_conv1_tc_kernel, dim3((unsigned)((o.L + kD0TcTile - 1) / kD0TcTile), o.B), 256, 0, st, reinterpret_cast<const float*>(o.in),
-                         (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], reinterpret_cast<__nv_bfloat16*>(o.out_t), o.stats_out, o.L, 1e-5f);
+                         (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], reinterpret_cast<__nv_bfloat16*>(o.out_t), o.stats_out, o.L, 1e-5f, (int)i);
               break;
             }
           }
@@ -1550,7 +1550,7 @@ struct Engine : EngineBase {
               launch_pdl(d0_tail_tc_kernel<2>, dim3((unsigned)((o.L + kD0TcTile - 1) / kD0TcTile), o.B), 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(o.in),
                          (const double*)o.stats_in, o.w0, o.w1, o.wx[0], o.wx[1], o.resid, sc.frow + o.ft_off, sc.bstride, sc.bmod,
                          reinterpret_cast<const __nv_bfloat16*>(o.in2), Bx, o.wx[2], o.wx[3], o.w2, XB_total, o.out_r, reinterpret_cast<__nv_bfloat16*>(o.out_t),
-                         o.stats_out, o.L, 1e-5f);
+                         o.stats_out, o.L, 1e-5f, (int)i);
               break;
             }
           }
